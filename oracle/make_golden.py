@@ -1,0 +1,202 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference on CPU.
+
+Run in the build container only (needs /root/reference or $SURF_REF):
+
+    python oracle/make_golden.py
+
+The reference has no golden vectors of its own, so these are
+outputs of the reference itself (imported from where it lies through
+oracle/ref_loader.py — nothing is copied) on small synthetic scenes built by
+surf_b200/synthetic.py.  Each file stores the network state_dict, the ray
+inputs, the scene recipe (regenerated from seeds at test time; a checksum of
+the scene tensors guards against generator drift) and every output tensor.
+"""
+import hashlib
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+
+import ref_loader  # noqa: E402
+from surf_b200 import synthetic  # noqa: E402
+from surf_b200.conf import default_implicit_surface_conf  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def scene_checksum(sc):
+    h = hashlib.sha256()
+    for t in [sc.imgs, sc.intrs, sc.c2ws, sc.near, sc.far, sc.matching_volume] + sc.volumes + sc.sparse_idxes \
+            + sc.mask_volumes + sc.features:
+        h.update(t.contiguous().numpy().tobytes())
+    return h.hexdigest()
+
+
+def build_reference_net(IS, weight_seed, perturb_weights, variance=None, scene=None):
+    conf = default_implicit_surface_conf()
+    torch.manual_seed(weight_seed)
+    net = IS.ImplicitSurface(conf)
+    if perturb_weights:
+        # geometric init zeroes every feature / PE-frequency column (sdf_network.py:71-86), which
+        # would leave the sparse-volume path untested: add noise to all parameters.
+        g = torch.Generator().manual_seed(weight_seed + 1)
+        with torch.no_grad():
+            for name, p in net.named_parameters():
+                if name.endswith("weight_v"):
+                    zero_cols = (p == 0).to(p.dtype)       # feature / PE-frequency columns
+                    p.add_(torch.randn(p.shape, generator=g) * (0.01 + 0.04 * zero_cols))
+                elif name.endswith("weight_g"):
+                    p.mul_(1.0 + 0.1 * torch.randn(p.shape, generator=g))
+                elif name.endswith("bias"):
+                    p.add_(torch.randn(p.shape, generator=g) * 0.02)
+        if scene is not None:
+            # the noise shifts the level set; re-centre it on the r=0.5 sphere so rays still cross a surface
+            q = torch.randn(512, 3, generator=g)
+            q = 0.5 * q / q.norm(dim=-1, keepdim=True)
+            with torch.no_grad():
+                shift = net.sdf_network.sdf(q, scene.volumes, scene.sparse_idxes).mean()
+                net.sdf_network.lin6.bias[0] -= shift
+    if variance is not None:
+        with torch.no_grad():
+            net.deviation_network.variance.fill_(variance)
+    net.eval()
+    return net
+
+
+def to_np(v):
+    if isinstance(v, torch.Tensor):
+        return v.detach().cpu().numpy()
+    return np.asarray(v)
+
+
+def save(name, recipe, net, inputs, outputs):
+    d = {}
+    for k, v in recipe.items():
+        d["recipe." + k] = np.asarray(v)
+    for k, v in net.state_dict().items():
+        d["sd." + k] = to_np(v)
+    for k, v in inputs.items():
+        d["in." + k] = to_np(v)
+    for k, v in outputs.items():
+        d["out." + k] = to_np(v)
+    d["torch_version"] = np.asarray(torch.__version__)
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **d)
+    print("wrote", path, "%.1f KB" % (os.path.getsize(path) / 1024))
+
+
+def case_render(IS, name, nv, H, W, base, scene_seed, n_rays, ray_seed, weight_seed, perturb_weights,
+                variance, torch_seed, miss=False):
+    sc = synthetic.make_scene(nv, H, W, base, seed=scene_seed)
+    net = build_reference_net(IS, weight_seed, perturb_weights, variance, sc)
+    o, d = synthetic.random_pixel_rays(sc, n_rays, seed=ray_seed)
+    if miss:
+        # rays that leave the volume immediately: exercises the empty-mask fallback (Q6)
+        o = o + torch.tensor([0.0, 0.0, -6.0])
+    near = sc.near.expand(n_rays, 1).contiguous()
+    far = sc.far.expand(n_rays, 1).contiguous()
+    torch.manual_seed(torch_seed)
+    out = net.render(o, d, near, far, *sc.render_args(), 1.0, None)
+    # stage outputs recomputed from the reference's own sub-functions on the same inputs
+    P = IS  # module namespace
+    mid_z = out["mid_z_vals"]
+    pts = (o[:, None, :] + d[:, None, :] * mid_z[..., :, None]).reshape(-1, 3)
+    vmask = P.lookup_volume(pts, sc.mask_volumes, sample_mode="nearest").any(dim=-1)
+    extra = {"_voxel_mask": vmask}
+    sel = vmask.clone()
+    if int(sel.sum()) < 1:
+        sel[:10] = True
+    pv = pts[sel]
+    from models.modules.projector import lookup_sparse_volume
+    extra["_pts_valid"] = pv
+    extra["_sparse_feats"] = lookup_sparse_volume(pv.clone(), sc.volumes, sc.sparse_idxes)
+    fv, rd, mv = P.lookup_feature(pv, sc.imgs, sc.intrs, sc.c2ws, sc.features)
+    extra["_feat_views"], extra["_ray_diff"], extra["_view_mask"] = fv, rd, mv
+    extra["_blend_rgb"] = net.color_network(fv.clone(), rd, mv)
+    extra["_sdf_full"] = net.sdf_network(pv, sc.volumes, sc.sparse_idxes)
+    gr, sm = net.sdf_network.gradient(pv.clone(), sc.volumes, sc.sparse_idxes)
+    extra["_grad_valid"], extra["_smooth_valid"] = gr, sm
+    out = {k: v for k, v in out.items()}
+    out.update(extra)
+    recipe = dict(nv=nv, H=H, W=W, base=base, scene_seed=scene_seed, torch_seed=torch_seed,
+                  scene_sha=scene_checksum(sc))
+    save(name, recipe, net, {"rays_o": o, "rays_d": d, "near": near, "far": far}, out)
+
+
+def case_validate(IS, name, nv, H, W, base, scene_seed, res_level, weight_seed, torch_seed):
+    sc = synthetic.make_scene(nv, H, W, base, seed=scene_seed)
+    net = build_reference_net(IS, weight_seed, True, None, sc)
+    o, d, hw = synthetic.image_rays(sc, res_level)
+    near = sc.near.expand(o.shape[0], 1).contiguous()
+    far = sc.far.expand(o.shape[0], 1).contiguous()
+    torch.manual_seed(torch_seed)
+    out = net.validate(o, d, near, far, *sc.render_args(), torch.tensor([-1.0, -1, -1]), torch.tensor([1.0, 1, 1]),
+                       hw, 1.0, None, extract_geometry=False)
+    recipe = dict(nv=nv, H=H, W=W, base=base, scene_seed=scene_seed, torch_seed=torch_seed,
+                  res_level=res_level, scene_sha=scene_checksum(sc))
+    save(name, recipe, net, {"rays_o": o, "rays_d": d, "near": near, "far": far}, out)
+
+
+def case_sdf_grid(IS, name, base, scene_seed, weight_seed, resolution):
+    sc = synthetic.make_scene(3, 48, 64, base, seed=scene_seed)
+    net = build_reference_net(IS, weight_seed, True, None, sc)
+    # extract_geometry's loop body (implicit_surface.py:339-351) without the marching-cubes call
+    bmin, bmax = torch.tensor([-1.0, -1, -1]), torch.tensor([1.0, 1, 1])
+    N = 64
+    X = torch.linspace(bmin[0], bmax[0], resolution).split(N)
+    Y = torch.linspace(bmin[1], bmax[1], resolution).split(N)
+    Z = torch.linspace(bmin[2], bmax[2], resolution).split(N)
+    u = np.zeros([resolution] * 3, dtype=np.float32)
+    with torch.no_grad():
+        for xi, xs in enumerate(X):
+            for yi, ys in enumerate(Y):
+                for zi, zs in enumerate(Z):
+                    xx, yy, zz = torch.meshgrid(xs, ys, zs, indexing="ij")
+                    pts = torch.cat([xx.reshape(-1, 1), yy.reshape(-1, 1), zz.reshape(-1, 1)], dim=-1)
+                    val = -net.sdf_network.sdf(pts, sc.volumes, sc.sparse_idxes).reshape(len(xs), len(ys), len(zs))
+                    u[xi * N: xi * N + len(xs), yi * N: yi * N + len(ys), zi * N: zi * N + len(zs)] = val.numpy()
+    # points outside [-1,1]^3 (extrapolating corner weights, Q13) and exactly on voxel centres
+    g = torch.Generator().manual_seed(5)
+    wild = (torch.rand(256, 3, generator=g) * 3.0 - 1.5)
+    n_fine = sc.sparse_idxes[0].shape[0]
+    centres = torch.randint(0, n_fine, (64, 3), generator=g).float() * (2.0 / (n_fine - 1)) - 1.0
+    wild = torch.cat([wild, centres, torch.tensor([[-1.0, -1, -1], [1, 1, 1], [0, 0, 0]])])
+    with torch.no_grad():
+        full = net.sdf_network(wild, sc.volumes, sc.sparse_idxes)
+    gr, sm = net.sdf_network.gradient(wild.clone(), sc.volumes, sc.sparse_idxes)
+    recipe = dict(nv=3, H=48, W=64, base=base, scene_seed=scene_seed, resolution=resolution,
+                  scene_sha=scene_checksum(sc))
+    save(name, recipe, net, {"wild_pts": wild}, {"u": u, "wild_full": full, "wild_grad": gr, "wild_smooth": sm})
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    IS = ref_loader.load_reference()
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    # A: DTU-shaped val (3 views), perturbed weights so every path matters
+    case_render(IS, "render_v2_perturbed", nv=3, H=48, W=64, base=8, scene_seed=1, n_rays=48, ray_seed=2,
+                weight_seed=0, perturb_weights=True, variance=None, torch_seed=0)
+    # B: pristine geometric init (sphere SDF), larger inv_s
+    case_render(IS, "render_v2_init", nv=3, H=48, W=64, base=8, scene_seed=3, n_rays=32, ray_seed=4,
+                weight_seed=0, perturb_weights=False, variance=0.8, torch_seed=7)
+    # C: training-shaped (5 views)
+    case_render(IS, "render_v4_perturbed", nv=5, H=60, W=80, base=8, scene_seed=11, n_rays=32, ray_seed=12,
+                weight_seed=3, perturb_weights=True, variance=0.5, torch_seed=5)
+    # D: rays missing the volume -> empty-mask fallback
+    case_render(IS, "render_miss", nv=3, H=48, W=64, base=8, scene_seed=1, n_rays=16, ray_seed=6,
+                weight_seed=0, perturb_weights=True, variance=None, torch_seed=1, miss=True)
+    # E: chunked validation image (3 chunks of 256 rays -> RNG stream across chunks, Q1)
+    case_validate(IS, "validate_24x32", nv=3, H=48, W=64, base=8, scene_seed=1, res_level=2, weight_seed=0,
+                  torch_seed=0)
+    # F: SDF grid + out-of-range points
+    case_sdf_grid(IS, "sdf_grid_24", base=8, scene_seed=1, weight_seed=0, resolution=24)
+
+
+if __name__ == "__main__":
+    main()

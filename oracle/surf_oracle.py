@@ -1,0 +1,602 @@
+"""CPU oracle: a restatement of SuRF's per-ray volume-rendering hot path.
+
+TEST INFRASTRUCTURE — NOT PRODUCT CODE.  Only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl
+reference`` legs may import this module, and only as the checker / the CPU
+baseline.  ``surf_b200/`` never imports it and has no CPU fallback.
+
+What it is: the algorithm of the reference's hot path (SURVEY.md §8a rows
+A1-A11) restated as plain functions over fp32 torch CPU tensors, each citing
+the reference file:line it follows.  It deliberately uses the same ATen
+primitives as the reference wherever a result is integer-sensitive
+(``F.grid_sample`` nearest / ``torch.linspace`` / ``torch.sort`` /
+``torch.inverse``), so on the same torch build it reproduces the reference
+bit-for-bit for masks and indices.
+
+Parity pin: ``oracle/make_golden.py`` imports the UNMODIFIED reference from
+``/root/reference`` (three import shims, ``oracle/ref_loader.py``), runs it on
+small synthetic scenes and stores inputs+outputs under ``tests/golden/``;
+``tests/test_oracle_golden.py`` checks this file against those vectors
+(integers bit-exact, floats <= 1e-5).  The reference ships no tests or golden
+vectors of its own.
+
+Not restated (SURVEY.md §8f "next", F1): the training-only extras
+``smooth`` (second-order autograd, sdf_network.py:143-150) and
+``surface_patch_warp2`` (projector.py:560-645).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence
+
+import torch
+import torch.nn.functional as F
+
+SQRT2 = math.sqrt(2.0)
+
+
+# ----------------------------------------------------------------------------------------------
+# parameters
+# ----------------------------------------------------------------------------------------------
+class OracleNet:
+    """Plain-tensor view of an ``ImplicitSurface`` state_dict (reference param names).
+
+    ``sd`` keys: ``sdf_network.lin{l}.{weight_g,weight_v,bias}`` (or ``.weight`` when not
+    weight-normed), ``color_network.*``, ``deviation_network.variance``.
+    """
+
+    def __init__(self, sd: Dict[str, torch.Tensor], n_samples=(64, 32, 24, 16),
+                 sample_ranges=(1.0, 0.4, 0.1, 0.01), n_depth=256, perturb=1.0,
+                 multires=4, skip_in=(3,), scale=1.0, n_layers=6):
+        sd = {k: v.detach().to(torch.float32).cpu() for k, v in sd.items()}
+        self.n_samples = [int(x) for x in n_samples]
+        self.sample_ranges = [float(x) for x in sample_ranges]
+        self.n_depth = int(n_depth)
+        self.perturb = float(perturb)
+        self.multires = int(multires)
+        self.skip_in = tuple(int(s) for s in skip_in)
+        self.scale = float(scale)
+        self.num_lin = n_layers + 1
+        self.W: List[torch.Tensor] = []
+        self.b: List[torch.Tensor] = []
+        for l in range(self.num_lin):
+            p = "sdf_network.lin%d." % l
+            if p + "weight_g" in sd:
+                # nn.utils.weight_norm(dim=0): W = g * v / ||v||_row   (sdf_network.py:88-89)
+                W = torch._weight_norm(sd[p + "weight_v"], sd[p + "weight_g"], 0)
+            else:
+                W = sd[p + "weight"]
+            self.W.append(W.contiguous())
+            self.b.append(sd[p + "bias"].contiguous())
+        c = "color_network."
+        self.color = {k[len(c):]: v for k, v in sd.items() if k.startswith(c)}
+        self.variance = sd["deviation_network.variance"].reshape(())
+
+
+# ----------------------------------------------------------------------------------------------
+# dense volume lookups  (projector.py:392-420)
+# ----------------------------------------------------------------------------------------------
+def lookup_dense(pts: torch.Tensor, volumes, mode: str) -> torch.Tensor:
+    """``F.grid_sample`` of (1,C,N,N,N) volumes at ``pts`` (n,3) -> (n, sum C).
+
+    Grid = pts flipped so world (x,y,z) <-> volume axes (D,H,W); default align_corners=False and
+    zero padding (projector.py:398,406,415; quirk Q4)."""
+    pts = pts.reshape(-1, 3)
+    n = pts.shape[0]
+    grid = pts.flip(-1)[None, None, None]
+    vols = [volumes] if isinstance(volumes, torch.Tensor) else list(volumes)
+    cols = []
+    for v in vols:
+        s = F.grid_sample(v, grid, mode=mode, align_corners=False)
+        cols.append(s.reshape(-1, n).t().contiguous())
+    return torch.cat(cols, dim=-1)
+
+
+def point_mask(pts: torch.Tensor, mask_volumes) -> torch.Tensor:
+    """voxel mask = nearest lookup in every level's 0/1 volume, OR-ed (implicit_surface.py:86; Q5)."""
+    return lookup_dense(pts, mask_volumes, "nearest").any(dim=-1)
+
+
+# ----------------------------------------------------------------------------------------------
+# sparse trilinear lookup  (projector.py:217-390; quirk Q13)
+# ----------------------------------------------------------------------------------------------
+def sparse_trilinear(volume: torch.Tensor, index: torch.Tensor, pts_zyx: torch.Tensor) -> torch.Tensor:
+    """volume (nvox,c), index (N,N,N) int64 (-1 empty), pts already flipped to (z,y,x) -> (n,c).
+
+    Differentiable w.r.t. ``pts_zyx`` through the interpolation weights only (corner indices are
+    integers), exactly like projector.py:238-283."""
+    n = pts_zyx.shape[0]
+    c = volume.shape[1]
+    dims = torch.tensor(list(index.shape), dtype=pts_zyx.dtype)
+    voxel = (torch.ones(3, dtype=pts_zyx.dtype) - (-torch.ones(3, dtype=pts_zyx.dtype))) / (dims - 1)
+    coords = (pts_zyx - (-torch.ones(3, dtype=pts_zyx.dtype))[None]) / voxel[None]     # :231-232
+    cx, cy, cz = coords[:, 0], coords[:, 1], coords[:, 2]
+    with torch.no_grad():
+        x0 = torch.floor(cx).long()
+        y0 = torch.floor(cy).long()
+        z0 = torch.floor(cz).long()
+    x1, y1, z1 = x0 + 1, y0 + 1, z0 + 1
+    IW, IH, ID = index.shape
+    flat = index.reshape(-1)
+    out = None
+    # corner order and weight expressions follow projector.py:274-283 / 360-371 (bnw ... fse)
+    for zz, wz_hi in ((z0, True), (z1, False)):
+        for yy, wy_hi in ((y0, True), (y1, False)):
+            for xx, wx_hi in ((x0, True), (x1, False)):
+                wx = (x1 - cx) if wx_hi else (cx - x0)
+                wy = (y1 - cy) if wy_hi else (cy - y0)
+                wz = (z1 - cz) if wz_hi else (cz - z0)
+                w = wx * wy * wz
+                with torch.no_grad():
+                    lin = (zz.clamp(0, ID - 1) * ID ** 2 + yy.clamp(0, IH - 1) * IW + xx.clamp(0, IW - 1))
+                    row = flat[lin]                                                   # :323-340
+                    ok = row != -1
+                val = torch.zeros(n, c, dtype=volume.dtype)
+                val[ok] = volume[row[ok]]                                             # :342-358
+                term = val * w[:, None]
+                out = term if out is None else out + term
+    return out
+
+
+def lookup_sparse(pts: torch.Tensor, volumes: Sequence[torch.Tensor], indexes: Sequence[torch.Tensor]):
+    """(n,3) -> (n, 7*levels); levels concatenated in the order given (fine->coarse) (:377-390)."""
+    p = pts.flip(-1)
+    return torch.cat([sparse_trilinear(v, i, p) for v, i in zip(volumes, indexes)], dim=-1)
+
+
+# ----------------------------------------------------------------------------------------------
+# SDF MLP  (sdf_network.py:95-152, embedder.py:6-51)
+# ----------------------------------------------------------------------------------------------
+def positional_encoding(x: torch.Tensor, multires: int) -> torch.Tensor:
+    if multires <= 0:
+        return x
+    outs = [x]
+    for f in 2.0 ** torch.linspace(0.0, multires - 1, multires):
+        outs.append(torch.sin(x * f))
+        outs.append(torch.cos(x * f))
+    return torch.cat(outs, dim=-1)
+
+
+def softplus100(x):
+    return F.softplus(x, beta=100)
+
+
+def sdf_forward(net: OracleNet, pts: torch.Tensor, volumes, indexes, feats: Optional[torch.Tensor] = None):
+    """Full (n,129) output of SDFNetworkSparse.forward (sdf_network.py:95-121)."""
+    if feats is None:
+        feats = lookup_sparse(pts.clone(), volumes, indexes)
+    pe = positional_encoding(pts * net.scale, net.multires)
+    h = pe
+    last = net.num_lin - 1
+    for l in range(net.num_lin):
+        if l in net.skip_in:
+            h = torch.cat([h, pe], dim=-1) / SQRT2
+        if 0 < l:
+            h = torch.cat([h, feats], dim=-1)
+        h = F.linear(h, net.W[l], net.b[l])
+        if l < last:
+            h = softplus100(h)
+    return torch.cat([h[:, :1] / net.scale, h[:, 1:]], dim=-1)
+
+
+def sdf_only(net: OracleNet, pts, volumes, indexes):
+    return sdf_forward(net, pts, volumes, indexes)[:, :1]
+
+
+def sdf_gradient(net: OracleNet, pts: torch.Tensor, volumes, indexes):
+    """d sdf / d x by autograd, like sdf_network.py:129-141 (first-order part only).
+
+    Returns (sdf (n,1), grad (n,3)), both detached."""
+    with torch.enable_grad():
+        x = pts.detach().clone().requires_grad_(True)
+        y = sdf_only(net, x, volumes, indexes)
+        (g,) = torch.autograd.grad(y, x, torch.ones_like(y))
+    return y.detach(), g.detach()
+
+
+def sdf_gradient_analytic(net: OracleNet, pts: torch.Tensor, volumes, indexes):
+    """The same gradient by an explicit reverse pass (the derivation the CUDA kernel implements).
+
+    dsdf/dx = J_pe^T g_pe + J_feat^T g_feat where g_pe collects the input-gradients of lin0 and of
+    the skip layer's PE columns, and g_feat those of the 28 feature columns of lin1..lin6."""
+    n = pts.shape[0]
+    p = pts.flip(-1)
+    # feature values and their Jacobian w.r.t. the *flipped* point, level by level
+    feats, jac = [], []
+    for vol, idx in zip(volumes, indexes):
+        N = idx.shape[0]
+        voxel = torch.tensor(2.0, dtype=torch.float32) / (torch.tensor(float(N)) - 1)
+        c = (p + 1.0) / voxel
+        i0 = torch.floor(c)
+        fr1 = c - i0                 # (coord - corner0)
+        fr0 = (i0 + 1) - c           # (corner1 - coord)
+        i0 = i0.long()
+        f = torch.zeros(n, vol.shape[1])
+        J = torch.zeros(n, vol.shape[1], 3)
+        flat = idx.reshape(-1)
+        for dz in (0, 1):
+            for dy in (0, 1):
+                for dx in (0, 1):
+                    wx = fr1[:, 0] if dx else fr0[:, 0]
+                    wy = fr1[:, 1] if dy else fr0[:, 1]
+                    wz = fr1[:, 2] if dz else fr0[:, 2]
+                    sx, sy, sz = (1.0 if dx else -1.0), (1.0 if dy else -1.0), (1.0 if dz else -1.0)
+                    lin = ((i0[:, 2] + dz).clamp(0, N - 1) * N * N + (i0[:, 1] + dy).clamp(0, N - 1) * N
+                           + (i0[:, 0] + dx).clamp(0, N - 1))
+                    row = flat[lin]
+                    ok = row != -1
+                    val = torch.zeros(n, vol.shape[1])
+                    val[ok] = vol[row[ok]]
+                    f += val * (wx * wy * wz)[:, None]
+                    J[:, :, 0] += val * (sx * wy * wz / voxel)[:, None]
+                    J[:, :, 1] += val * (wx * sy * wz / voxel)[:, None]
+                    J[:, :, 2] += val * (wx * wy * sz / voxel)[:, None]
+        feats.append(f)
+        jac.append(J)
+    feats = torch.cat(feats, dim=1)
+    jac = torch.cat(jac, dim=1)                      # (n, 28, 3) in flipped (z,y,x) order
+    x = pts * net.scale
+    pe = positional_encoding(x, net.multires)
+    last = net.num_lin - 1
+    h = pe
+    sig = []
+    nfeat = feats.shape[1]
+    for l in range(net.num_lin):
+        if l in net.skip_in:
+            h = torch.cat([h, pe], dim=-1) / SQRT2
+        if l > 0:
+            h = torch.cat([h, feats], dim=-1)
+        z = F.linear(h, net.W[l], net.b[l])
+        if l < last:
+            sig.append(torch.sigmoid(100.0 * z))     # softplus'(z), beta=100
+            h = softplus100(z)
+        else:
+            h = z
+    sdf = h[:, :1] / net.scale
+    # reverse pass
+    g_pe = torch.zeros(n, pe.shape[1])
+    g_feat = torch.zeros(n, nfeat)
+    delta = torch.zeros(n, net.W[last].shape[0])
+    delta[:, 0] = 1.0 / net.scale
+    for l in range(last, -1, -1):
+        if l < last:
+            delta = delta * sig[l]
+        gin = delta @ net.W[l]                       # gradient w.r.t. this layer's input
+        if l > 0:
+            g_feat += gin[:, -nfeat:]
+            gin = gin[:, :-nfeat]
+        if l in net.skip_in:
+            gin = gin / SQRT2
+            g_pe += gin[:, -pe.shape[1]:]
+            gin = gin[:, :-pe.shape[1]]
+        if l == 0:
+            g_pe += gin
+        delta = gin
+    # d PE / d x
+    gx = g_pe[:, 0:3].clone()
+    k = 3
+    for f in 2.0 ** torch.linspace(0.0, net.multires - 1, net.multires):
+        gx += g_pe[:, k:k + 3] * torch.cos(x * f) * f
+        gx -= g_pe[:, k + 3:k + 6] * torch.sin(x * f) * f
+        k += 6
+    gx = gx * net.scale
+    gp = torch.einsum("nc,ncd->nd", g_feat, jac)     # w.r.t. flipped point
+    return sdf, gx + gp.flip(-1)
+
+
+# ----------------------------------------------------------------------------------------------
+# multi-view projection + gather  (projector.py:485-556; quirk Q14)
+# ----------------------------------------------------------------------------------------------
+def ray_direction_diff(pts, ref_c2w, src_c2ws):
+    """(n,3) -> (n,V,4): [normalised difference of unit vectors to ref/src centres, their dot]."""
+    to_ref = ref_c2w[None, :3, 3] - pts                                  # (n,3)
+    to_ref = to_ref / (torch.norm(to_ref, dim=-1, keepdim=True) + 1e-6)
+    to_src = src_c2ws[:, None, :3, 3] - pts[None]                        # (V,n,3)
+    to_src = to_src / (torch.norm(to_src, dim=-1, keepdim=True) + 1e-6)
+    diff = to_ref[None] - to_src
+    dot = (to_ref[None] * to_src).sum(-1, keepdim=True)
+    direction = diff / torch.clamp(torch.norm(diff, dim=-1, keepdim=True), min=1e-6)
+    return torch.cat([direction, dot], dim=-1).permute(1, 0, 2).contiguous()
+
+
+def lookup_feature(pts, imgs, intrs, c2ws, features):
+    """-> feat_views (n,V,19) = [rgb3, f0(4), f1(4), f2(4), f3(4)], ray_diff (n,V,4), mask (n,V) bool."""
+    src_K, src_c2w, ref_c2w = intrs[1:], c2ws[1:], c2ws[0]
+    V = src_K.shape[0]
+    n = pts.shape[0]
+    ray_diff = ray_direction_diff(pts, ref_c2w, src_c2w)
+    homog = torch.cat([pts.t().contiguous(), torch.ones(1, n)], dim=0)    # (4,n)
+    cam = torch.matmul(torch.inverse(src_c2w), homog[None])[:, :3]        # (V,3,n)   :529
+    feats_per_level = []
+    mask_all = None
+    rgb = None
+    for i, feat in enumerate(features):
+        K = src_K.clone()
+        K[:, :2] = K[:, :2] * (0.5 ** i)                                  # :525
+        h, w = feat.shape[-2:]
+        uvw = torch.matmul(K[:, :3, :3], cam)                             # :530
+        xy = uvw[:, :2] / uvw[:, 2:]                                      # no guard on w (:531)
+        gx = xy[:, 0] / ((w - 1) / 2) - 1
+        gy = xy[:, 1] / ((h - 1) / 2) - 1
+        m = (uvw[:, 2] > 0) & (xy[:, 0] >= 0) & (xy[:, 0] < w) & (xy[:, 1] >= 0) & (xy[:, 1] < h)
+        m = m.t()
+        mask_all = m if mask_all is None else (mask_all & m)
+        grid = torch.stack([gx, gy], dim=-1)[:, :, None]                  # (V,n,1,2)
+        s = F.grid_sample(feat[1:], grid, mode="bilinear", padding_mode="zeros", align_corners=False)
+        feats_per_level.append(s.reshape(V, feat.shape[1], n).permute(2, 0, 1))
+        if i == 0:
+            s = F.grid_sample(imgs[1:], grid, mode="bilinear", padding_mode="zeros", align_corners=False)
+            rgb = s.reshape(V, 3, n).permute(2, 0, 1)
+    return torch.cat([rgb] + feats_per_level, dim=2).contiguous(), ray_diff, mask_all.contiguous()
+
+
+# ----------------------------------------------------------------------------------------------
+# colour blending MLP  (blending_network.py:69-117)
+# ----------------------------------------------------------------------------------------------
+def _seq(x, cw, name, idxs, final_act=True):
+    for j, i in enumerate(idxs):
+        x = F.linear(x, cw["%s.%d.weight" % (name, i)], cw["%s.%d.bias" % (name, i)])
+        if final_act or j + 1 < len(idxs):
+            x = F.elu(x)
+    return x
+
+
+def blend(net: OracleNet, feat_views, ray_diff, mask):
+    cw = net.color
+    m = mask[:, :, None].to(feat_views.dtype)
+    V = feat_views.shape[1]
+    rgb_in = feat_views[..., :3]
+    x = feat_views + _seq(ray_diff, cw, "ray_dir_fc", (0, 2))
+    dot = ray_diff[..., 3:4]
+    e = torch.exp(torch.abs(cw["s"]) * (dot - 1))
+    wgt = (e - torch.min(e, dim=1, keepdim=True)[0]) * m
+    wgt = wgt / (torch.sum(wgt, dim=1, keepdim=True) + 1e-8)
+    mean = torch.sum(x * wgt, dim=1, keepdim=True)
+    var = torch.sum(wgt * (x - mean) ** 2, dim=1, keepdim=True)
+    g = torch.cat([mean, var], dim=-1).expand(-1, V, -1)
+    y = _seq(torch.cat([g, x], dim=-1), cw, "base_fc", (0, 2))
+    yv = _seq(y * wgt, cw, "vis_fc", (0, 2))
+    res, vis = yv[..., :-1], yv[..., -1:]
+    vis = torch.sigmoid(vis) * m
+    y = y + res
+    v2 = F.linear(F.elu(F.linear(y * vis, cw["vis_fc2.0.weight"], cw["vis_fc2.0.bias"])),
+                  cw["vis_fc2.2.weight"], cw["vis_fc2.2.bias"])
+    vis = torch.sigmoid(v2) * m
+    z = torch.cat([y, vis, ray_diff], dim=-1)
+    z = F.elu(F.linear(z, cw["rgb_fc.0.weight"], cw["rgb_fc.0.bias"]))
+    z = F.elu(F.linear(z, cw["rgb_fc.2.weight"], cw["rgb_fc.2.bias"]))
+    z = F.linear(z, cw["rgb_fc.4.weight"], cw["rgb_fc.4.bias"])
+    z = z.masked_fill(m == 0, -1e9)
+    bw = F.softmax(z, dim=1)
+    return torch.sum(rgb_in * bw, dim=1)
+
+
+# ----------------------------------------------------------------------------------------------
+# ray sampling  (implicit_surface.py:268-311; quirks Q1-Q3)
+# ----------------------------------------------------------------------------------------------
+def draw_t_rand(batch, n_stages=4):
+    """Draws the per-stage jitter from torch's global CPU generator in the reference's order:
+    one rand([B,1]) per stage (implicit_surface.py:276,305).  Returns (B, n_stages) in [0,1)."""
+    return torch.cat([torch.rand([batch, 1]) for _ in range(n_stages)], dim=1)
+
+
+def sample_z(net: OracleNet, rays_o, rays_d, near, far, matching_volume, t_rand: Optional[torch.Tensor]):
+    """-> sorted z_vals (B, sum n_samples), surf_z (B,1).  ``t_rand`` (B,4) in [0,1) (raw rand, the
+    0.5 shift is applied here); None or perturb<=0 -> no jitter."""
+    B = rays_o.shape[0]
+    n0 = net.n_samples[0]
+    jitter = net.perturb > 0 and t_rand is not None
+    lin = torch.linspace(0.0, 1.0, n0)
+    z0 = near + (far - near) * lin[None, :]
+    if jitter:
+        z0 = z0 + (t_rand[:, 0:1] - 0.5) * 2.0 / n0
+    stages = [z0]
+    span = far - near
+    lin = torch.linspace(0.0, 1.0, net.n_depth)
+    zp = near + (far - near) * lin[None, :]
+    pts = (rays_o[:, None, :] + rays_d[:, None, :] * zp[..., :, None]).reshape(-1, 3)
+    logit = lookup_dense(pts, matching_volume, "bilinear").reshape(B, -1)
+    w = F.softmax(logit, dim=-1)
+    surf_z = (zp * w).sum(dim=1, keepdim=True)
+    for s, (ratio, n) in enumerate(zip(net.sample_ranges[1:], net.n_samples[1:]), start=1):
+        lo = surf_z - span * ratio
+        hi = surf_z + span * ratio
+        lo = torch.where(hi > far, lo - (hi - far), lo)
+        hi = torch.where(lo < near, hi + (near - lo), hi)
+        lo = torch.clamp(lo, near, far)
+        hi = torch.clamp(hi, near, far)
+        lin = torch.linspace(0.0, 1.0, n)
+        zs = lo + (hi - lo) * lin[None, :]
+        if jitter:
+            zs = zs + (t_rand[:, s:s + 1] - 0.5) * (hi - lo) / n
+        stages.append(zs)
+    z, _ = torch.sort(torch.cat(stages, dim=-1), dim=-1)
+    return z, surf_z
+
+
+# ----------------------------------------------------------------------------------------------
+# render_core  (implicit_surface.py:64-266; quirks Q2, Q5-Q12)
+# ----------------------------------------------------------------------------------------------
+def render_core(net: OracleNet, rays_o, rays_d, z_vals, volumes, indexes, mask_volumes, features,
+                imgs, intrs, c2ws, cos_anneal_ratio=1.0, pts_random: Optional[torch.Tensor] = None,
+                return_stages=False):
+    B, S = z_vals.shape
+    sample_dist = 2.0 / net.n_samples[0]
+    dists = z_vals[:, 1:] - z_vals[:, :-1]
+    dists = torch.cat([dists, torch.full((B, 1), sample_dist, dtype=z_vals.dtype)], dim=-1)
+    mid_z = z_vals + dists * 0.5
+    pts = (rays_o[:, None, :] + rays_d[:, None, :] * mid_z[..., :, None]).reshape(-1, 3)
+    dirs = rays_d[:, None, :].expand(B, S, 3).reshape(-1, 3)
+
+    vmask = point_mask(pts, mask_volumes)                     # bool (P,)
+    compute = vmask.clone()
+    if int(compute.sum()) < 1:                                # Q6 (implicit_surface.py:88-89)
+        compute[:10] = True
+    vmask_f = vmask.to(torch.float32)
+
+    P = pts.shape[0]
+    sdf = torch.full((P, 1), 100.0)                           # Q7
+    grad = torch.zeros(P, 3)
+    color = torch.zeros(P, 3)
+    view_mask = torch.zeros(P, imgs.shape[0] - 1, dtype=torch.bool)
+    pv = pts[compute]
+    s_v, g_v = sdf_gradient(net, pv, volumes, indexes)
+    sdf[compute] = s_v
+    grad[compute] = g_v
+    fv, rd, mv = lookup_feature(pv, imgs, intrs, c2ws, features)
+    color[compute] = blend(net, fv, rd, mv)
+    view_mask[compute] = mv
+    valid_mask = ((view_mask.reshape(B, S, -1).float().sum(dim=2) > 1).float().sum(dim=1, keepdim=True) > 8)  # Q11
+
+    inv_s = torch.exp(net.variance * 10.0).clip(1e-6, 1e6)    # Q9
+    true_cos = (dirs * grad).sum(-1, keepdim=True)
+    r = cos_anneal_ratio
+    iter_cos = -(F.relu(-true_cos * 0.5 + 0.5) * (1.0 - r) + F.relu(-true_cos) * r)
+    iter_cos = iter_cos * vmask_f[:, None]
+    step = iter_cos.clip(-10.0, 10.0) * dists.reshape(-1, 1) * 0.5
+    prev_cdf = torch.sigmoid((sdf - step) * inv_s)
+    next_cdf = torch.sigmoid((sdf + step) * inv_s)
+    alpha = (((prev_cdf - next_cdf) + 1e-5) / (prev_cdf + 1e-5)).reshape(B, S).clip(0.0, 1.0)
+    alpha = alpha * vmask_f.reshape(B, S)
+
+    pnorm = torch.linalg.norm(pts, ord=2, dim=-1).reshape(B, S)
+    inside = (pnorm < 1.0).float() * vmask_f.reshape(B, S)
+    relax_inside = (pnorm < 1.2).float() * vmask_f.reshape(B, S)
+
+    trans = torch.cumprod(torch.cat([torch.ones(B, 1), 1.0 - alpha + 1e-7], dim=-1), dim=-1)[:, :-1]
+    weights = alpha * trans
+    weight_sum = weights.sum(dim=-1, keepdim=True)
+    color_fine = (color.reshape(B, S, 3) * weights[:, :, None]).sum(dim=1)
+    g3 = grad.reshape(B, S, 3)
+    rot = torch.inverse(c2ws[0, :3, :3])
+    normal = torch.matmul(rot[None], (g3 * weights[:, :, None]).sum(dim=1)[:, :, None]).squeeze(-1)
+    cam_d = torch.matmul(rot[None], rays_d[:, :, None]).squeeze(-1)
+    render_depth = (mid_z * weights).sum(dim=1) * cam_d[:, 2]        # Q10
+
+    gerr = (torch.linalg.norm(g3, ord=2, dim=-1) - 1.0) ** 2
+    gradient_error = (relax_inside * gerr).sum() / (relax_inside.sum() + 1e-5)
+
+    # 1024 uniform random points -> sparse_sdf (implicit_surface.py:174-178); draws from the
+    # global generator unless given, to keep the RNG stream of chunked validation in step (Q1)
+    if pts_random is None:
+        pts_random = torch.rand([1024, 3]) * 2 - 1
+    rmask = point_mask(pts_random, mask_volumes)
+    sdf_random = torch.zeros(pts_random.shape[0], 1)
+    if bool(rmask.any()):
+        sdf_random[rmask] = sdf_only(net, pts_random[rmask], volumes, indexes)
+
+    # first SDF zero-crossing (Q12, implicit_surface.py:181-216)
+    sd = sdf.reshape(B, S)
+    vm = vmask_f.reshape(B, S)
+    both = ((vm[:, :-1] * vm[:, 1:]) > 0).float()
+    cross = (sd[:, :-1] * sd[:, 1:] <= 0).float()
+    rank = torch.arange(S - 1, 0, -1, dtype=torch.float32)          # S-1 ... 1: earliest wins
+    score = cross * rank[None, :] * both
+    i0 = torch.argmax(score, dim=1, keepdim=True)
+    i1 = i0 + 1
+    mid_inside = (0.5 * (torch.gather(inside, 1, i0) + torch.gather(inside, 1, i1)) > 0.5).float()
+    mid_inside = mid_inside * (score.sum(dim=1, keepdim=True) > 0).float()
+    ga = torch.gather(g3, 1, i0[:, :, None].expand(-1, -1, 3))
+    gb = torch.gather(g3, 1, i1[:, :, None].expand(-1, -1, 3))
+    cosab = (ga * gb).sum(-1) / (torch.linalg.norm(ga, ord=2, dim=-1) * torch.linalg.norm(gb, ord=2, dim=-1) + 1e-8)
+    mid_inside = mid_inside * (cosab > 0.5)
+    s1, s2 = torch.gather(sd, 1, i0), torch.gather(sd, 1, i1)
+    za, zb = torch.gather(mid_z, 1, i0), torch.gather(mid_z, 1, i1)
+    z_cross = (s1 * zb - s2 * za) / (s1 - s2 + 1e-10)
+    sdf_depth = z_cross * cam_d[:, None, 2] * mid_inside
+
+    out = {
+        "color_fine": color_fine,
+        "render_depth": render_depth,
+        "sdf_depth": sdf_depth,
+        "normal": normal,
+        "valid_mask": valid_mask,
+        "sparse_sdf": torch.cat([sdf_random, sdf]),
+        "mid_z_vals": mid_z,
+        "gradients": g3,
+        "s_val": (1.0 / inv_s).reshape(1, 1).expand(P, 1),
+        "weights": weights,
+        "weight_sum": weight_sum,
+        "weight_max": torch.max(weights, dim=-1, keepdim=True)[0],
+        "gradient_error": gradient_error,
+        "inside_sphere": inside,
+        "mid_inside_sphere": mid_inside,
+    }
+    if return_stages:
+        out.update({"_pts": pts, "_voxel_mask": vmask, "_compute_mask": compute, "_sdf": sdf,
+                    "_color": color.reshape(B, S, 3), "_view_mask": view_mask, "_alpha": alpha,
+                    "_prev_idx": i0, "_dists": dists})
+    return out
+
+
+def render(net: OracleNet, rays_o, rays_d, near, far, matching_volume, volumes, indexes, mask_volumes,
+           imgs, features, intrs, c2ws, cos_anneal_ratio=1.0, t_rand=None, pts_random=None,
+           return_stages=False):
+    """ImplicitSurface.render (implicit_surface.py:268-335).  With t_rand/pts_random = None the
+    jitter and the random points are drawn from torch's global CPU generator in the reference's
+    order (Q1), so ``torch.manual_seed(s); render(...)`` matches the reference stream."""
+    if near.shape[0] == 1 and rays_o.shape[0] != 1:
+        near = near.expand(rays_o.shape[0], 1)
+        far = far.expand(rays_o.shape[0], 1)
+    if t_rand is None and net.perturb > 0:
+        t_rand = draw_t_rand(rays_o.shape[0], len(net.n_samples))
+    z, surf_z = sample_z(net, rays_o, rays_d, near, far, matching_volume, t_rand)
+    out = render_core(net, rays_o, rays_d, z, volumes, indexes, mask_volumes, features, imgs, intrs, c2ws,
+                      cos_anneal_ratio, pts_random, return_stages)
+    if return_stages:
+        out["_z_vals"] = z
+        out["_surf_z"] = surf_z
+    return out
+
+
+def validate_image(net: OracleNet, rays_o, rays_d, near, far, matching_volume, volumes, indexes,
+                   mask_volumes, imgs, features, intrs, c2ws, hw, cos_anneal_ratio=1.0, chunk=256):
+    """The image part of ImplicitSurface.validate (implicit_surface.py:366-400): 256-ray chunks."""
+    import numpy as np
+    if near.shape[0] == 1:
+        near = near.expand(rays_o.shape[0], 1)
+        far = far.expand(rays_o.shape[0], 1)
+    rgb, nrm, sd, rd = [], [], [], []
+    for o, d, n, f in zip(rays_o.split(chunk), rays_d.split(chunk), near.split(chunk), far.split(chunk)):
+        r = render(net, o, d, n, f, matching_volume, volumes, indexes, mask_volumes, imgs, features, intrs,
+                   c2ws, cos_anneal_ratio)
+        rgb.append(r["color_fine"])
+        nn_ = (r["gradients"] * r["weights"][:, :, None] * r["inside_sphere"][..., None]).sum(dim=1)
+        nrm.append(nn_.numpy())
+        sd.append(r["sdf_depth"].numpy())
+        rd.append(r["render_depth"].numpy())
+    h, w = int(hw[0]), int(hw[1])
+    color = torch.cat(rgb, dim=0)
+    rot = np.linalg.inv(c2ws[0, :3, :3].numpy())
+    normal = np.concatenate(nrm, axis=0)
+    return {
+        "color_fine": color,
+        "img_fine": (color.numpy().reshape(h, w, 3) * 256).clip(0, 255),
+        "normal_img": (np.matmul(rot[None], normal[:, :, None]).reshape(h, w, 3) * 128 + 128).clip(0, 255),
+        "sdf_depth": np.concatenate(sd, axis=0).reshape(h, w),
+        "render_depth": np.concatenate(rd, axis=0).reshape(h, w),
+    }
+
+
+def sdf_grid(net: OracleNet, volumes, indexes, bound_min, bound_max, resolution,
+             x_range=None, y_range=None, z_range=None, block=64):
+    """u = -sdf on the linspace grid of extract_geometry (implicit_surface.py:337-351), dense (Q16).
+    Optional index ranges restrict to a sub-box; returns u of that sub-box."""
+    X = torch.linspace(float(bound_min[0]), float(bound_max[0]), resolution)
+    Y = torch.linspace(float(bound_min[1]), float(bound_max[1]), resolution)
+    Z = torch.linspace(float(bound_min[2]), float(bound_max[2]), resolution)
+    xr = x_range or (0, resolution)
+    yr = y_range or (0, resolution)
+    zr = z_range or (0, resolution)
+    X, Y, Z = X[xr[0]:xr[1]], Y[yr[0]:yr[1]], Z[zr[0]:zr[1]]
+    u = torch.zeros(len(X), len(Y), len(Z))
+    with torch.no_grad():
+        for xi in range(0, len(X), block):
+            for yi in range(0, len(Y), block):
+                for zi in range(0, len(Z), block):
+                    xs, ys, zs = X[xi:xi + block], Y[yi:yi + block], Z[zi:zi + block]
+                    xx, yy, zz = torch.meshgrid(xs, ys, zs, indexing="ij")
+                    p = torch.stack([xx.reshape(-1), yy.reshape(-1), zz.reshape(-1)], dim=-1)
+                    v = -sdf_only(net, p, volumes, indexes).reshape(len(xs), len(ys), len(zs))
+                    u[xi:xi + len(xs), yi:yi + len(ys), zi:zi + len(zs)] = v
+    return u

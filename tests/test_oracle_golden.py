@@ -1,0 +1,96 @@
+"""Pins oracle/surf_oracle.py against outputs of the UNMODIFIED reference (tests/golden/*.npz,
+made by oracle/make_golden.py).  Integers bit-exact; floats <= 1e-5 scale-relative (the oracle
+uses the same ATen ops, differences are summation-order only)."""
+import numpy as np
+import pytest
+import torch
+
+import surf_oracle as O
+from helpers import assert_close, assert_equal_int, load_golden, scene_from_recipe
+
+TOL = 1e-5
+RENDER_CASES = ["render_v2_perturbed", "render_v2_init", "render_v4_perturbed", "render_miss"]
+
+
+def _net(g):
+    return O.OracleNet(g["sd"])
+
+
+@pytest.mark.parametrize("name", RENDER_CASES)
+def test_render_matches_reference(name):
+    g = load_golden(name)
+    sc = scene_from_recipe(g["recipe"])
+    net = _net(g)
+    i = g["in"]
+    torch.manual_seed(int(g["recipe"]["torch_seed"]))
+    out = O.render(net, i["rays_o"], i["rays_d"], i["near"], i["far"], sc.matching_volume, sc.volumes,
+                   sc.sparse_idxes, sc.mask_volumes, sc.imgs, sc.features, sc.intrs, sc.c2ws, 1.0,
+                   return_stages=True)
+    ref = g["out"]
+    assert_equal_int(out["_voxel_mask"], ref["_voxel_mask"], "voxel_mask")
+    assert_equal_int(out["valid_mask"], ref["valid_mask"], "valid_mask")
+    assert_equal_int(out["inside_sphere"], ref["inside_sphere"], "inside_sphere")
+    assert_equal_int(out["mid_inside_sphere"], ref["mid_inside_sphere"], "mid_inside_sphere")
+    assert_equal_int(out["_view_mask"][out["_compute_mask"]], ref["_view_mask"], "view_mask")
+    assert np.array_equal(out["mid_z_vals"].numpy(), ref["mid_z_vals"]), "mid_z_vals must be bit-identical"
+    for k in ["color_fine", "render_depth", "sdf_depth", "normal", "gradients", "weights", "weight_sum",
+              "weight_max", "sparse_sdf", "s_val", "gradient_error"]:
+        assert_close(out[k], ref[k], TOL, k)
+
+
+@pytest.mark.parametrize("name", RENDER_CASES)
+def test_stage_functions_match_reference(name):
+    g = load_golden(name)
+    sc = scene_from_recipe(g["recipe"])
+    net = _net(g)
+    ref = g["out"]
+    pv = torch.from_numpy(ref["_pts_valid"])
+    feats = O.lookup_sparse(pv, sc.volumes, sc.sparse_idxes)
+    assert_close(feats, ref["_sparse_feats"], 1e-6, "sparse feats")
+    fv, rd, mv = O.lookup_feature(pv, sc.imgs, sc.intrs, sc.c2ws, sc.features)
+    assert_equal_int(mv, ref["_view_mask"], "view mask")
+    assert_close(fv, ref["_feat_views"], 1e-6, "feat_views")
+    assert_close(rd, ref["_ray_diff"], 1e-6, "ray_diff")
+    rgb = O.blend(net, torch.from_numpy(ref["_feat_views"]), torch.from_numpy(ref["_ray_diff"]),
+                  torch.from_numpy(ref["_view_mask"]))
+    assert_close(rgb, ref["_blend_rgb"], TOL, "blend rgb")
+    full = O.sdf_forward(net, pv, sc.volumes, sc.sparse_idxes)
+    assert_close(full, ref["_sdf_full"], TOL, "sdf full output")
+    s, gr = O.sdf_gradient(net, pv, sc.volumes, sc.sparse_idxes)
+    assert_close(gr, ref["_grad_valid"], TOL, "sdf gradient (autograd)")
+    s2, gr2 = O.sdf_gradient_analytic(net, pv, sc.volumes, sc.sparse_idxes)
+    assert_close(gr2, ref["_grad_valid"], 2e-5, "sdf gradient (analytic reverse pass)")
+    assert_close(s2, ref["_sdf_full"][:, :1], TOL, "sdf (analytic path)")
+
+
+def test_validate_image_matches_reference():
+    g = load_golden("validate_24x32")
+    sc = scene_from_recipe(g["recipe"])
+    net = _net(g)
+    i = g["in"]
+    r = int(g["recipe"]["res_level"])
+    hw = (sc.H // r, sc.W // r)
+    torch.manual_seed(int(g["recipe"]["torch_seed"]))
+    out = O.validate_image(net, i["rays_o"], i["rays_d"], i["near"], i["far"], sc.matching_volume, sc.volumes,
+                           sc.sparse_idxes, sc.mask_volumes, sc.imgs, sc.features, sc.intrs, sc.c2ws, hw)
+    for k in ["color_fine", "img_fine", "normal_img", "sdf_depth", "render_depth"]:
+        assert_close(out[k], g["out"][k], TOL, k)
+
+
+def test_sdf_grid_matches_reference():
+    g = load_golden("sdf_grid_24")
+    sc = scene_from_recipe(g["recipe"])
+    net = _net(g)
+    res = int(g["recipe"]["resolution"])
+    u = O.sdf_grid(net, sc.volumes, sc.sparse_idxes, [-1, -1, -1], [1, 1, 1], res)
+    assert_close(u, g["out"]["u"], TOL, "u grid")
+    sub = O.sdf_grid(net, sc.volumes, sc.sparse_idxes, [-1, -1, -1], [1, 1, 1], res, x_range=(5, 11),
+                     z_range=(3, 20))
+    assert_close(sub, g["out"]["u"][5:11, :, 3:20], TOL, "u sub-box")
+    wild = g["in"]["wild_pts"]
+    full = O.sdf_forward(net, wild, sc.volumes, sc.sparse_idxes)
+    assert_close(full, g["out"]["wild_full"], TOL, "out-of-range points")
+    _, gr = O.sdf_gradient(net, wild, sc.volumes, sc.sparse_idxes)
+    assert_close(gr, g["out"]["wild_grad"], TOL, "out-of-range gradient")
+    _, gr2 = O.sdf_gradient_analytic(net, wild, sc.volumes, sc.sparse_idxes)
+    assert_close(gr2, g["out"]["wild_grad"], 2e-5, "out-of-range gradient (analytic)")
