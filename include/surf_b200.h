@@ -1,0 +1,210 @@
+/* surf_b200 — C ABI of the B200-native SuRF volume-rendering hot path.
+ *
+ * One shared library (surf_b200/csrc/libsurf_b200.so, sm_100a only).  Plain
+ * pointers and sizes; no torch / C++ types cross this boundary.  The reference
+ * has no FFI on this path: its boundary is the Python module API of
+ * models/modules/implicit_surface.py.  Each entry point below names the
+ * reference interface it replaces (paths relative to the reference root); the
+ * Python mirror in surf_b200/modules/ binds them through ctypes
+ * (INTEGRATION.md shows the binding a maintainer would add).
+ *
+ * Conventions
+ *  - Every `const T* d_...` / `T* d_...` argument is DEVICE memory owned by the
+ *    caller (PyTorch allocates it); `h_...` is HOST memory.  The library never
+ *    frees or retains caller buffers.  The only library-owned device memory
+ *    lives behind the opaque `surf_scene` / `surf_net` handles (explicit
+ *    create/destroy).
+ *  - All work is enqueued on the caller's `stream` (a cudaStream_t passed as
+ *    void*); calls are asynchronous and re-entrant, no host sync inside unless
+ *    stated.
+ *  - Return code: 0 = ok, < 0 = invalid argument, > 0 = cudaError_t.  Nothing
+ *    throws across the ABI; `surf_last_error()` returns a thread-local message.
+ *  - There is NO CPU fallback: without a CUDA device every compute entry point
+ *    returns an error.
+ */
+#ifndef SURF_B200_H
+#define SURF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SURF_ABI_VERSION 1
+#define SURF_MAX_LEVELS 4
+#define SURF_MAX_VIEWS 8       /* source views (nv-1) */
+#define SURF_MAX_STAGES 4
+#define SURF_SDF_LAYERS 7      /* lin0..lin6 (sdf_network.py:45-91, n_layers=6) */
+
+typedef struct surf_scene surf_scene; /* opaque: prepared scene tensors */
+typedef struct surf_net surf_net;     /* opaque: folded / re-laid-out network weights */
+
+/* ---- scene ------------------------------------------------------------------------------
+ * Inputs are the reference-layout tensors SuRF.build_volumes emits (surf.py:80-131,
+ * volume.py:99-132) in RENDERER order (lists already reversed, surf.py:159):
+ * volume lists fine->coarse, feature lists high-res->low-res. */
+typedef struct surf_scene_inputs {
+  int32_t n_levels;                             /* 1..4 */
+  int32_t feat_ch;                              /* channels per level (7) */
+  int32_t dim[SURF_MAX_LEVELS];                 /* cubic volume dim N_l */
+  int64_t n_vox[SURF_MAX_LEVELS];               /* rows of volumes[l] */
+  const float* d_volumes[SURF_MAX_LEVELS];      /* (n_vox_l, feat_ch) fp32            surf.py:119 */
+  const int64_t* d_sparse_idx[SURF_MAX_LEVELS]; /* (N,N,N) int64, -1 = empty          volume.py:123-132 */
+  const float* d_mask_volumes[SURF_MAX_LEVELS]; /* (1,1,N,N,N) fp32 0/1               volume.py:112-119 */
+  const float* d_matching_volume;               /* (1,1,M,M,M) fp32 logits, may be NULL (no sampler) */
+  int32_t match_dim;
+  int32_t n_views;                              /* nv (reference view 0 + sources) */
+  int32_t img_h, img_w;
+  int32_t n_feat_levels;                        /* 4 */
+  const float* d_imgs;                          /* (nv,3,H,W) fp32                    dtu.py:318,384 */
+  const float* d_features[4];                   /* (nv,4,H>>i,W>>i) fp32 NCHW         feature_network.py:178 */
+  const float* h_intrs;                         /* HOST (nv,4,4) row-major */
+  const float* h_w2cs;                          /* HOST (nv,4,4) = inverse(c2ws), computed by the caller
+                                                   with the same routine as the reference (torch.inverse,
+                                                   projector.py:529) */
+  const float* h_c2ws;                          /* HOST (nv,4,4) */
+} surf_scene_inputs;
+
+typedef struct surf_scene_stats {
+  int64_t bytes_index, bytes_volumes, bytes_masks, bytes_matching, bytes_images;
+  int64_t n_vox[SURF_MAX_LEVELS];
+} surf_scene_stats;
+
+/* scene_prepare: int64->int32 index tables, fp32->1-bit masks, 7->8-float voxel rows,
+ * NCHW->NHWC feature maps (level 0 fused with RGB into 32-byte texels).  Replaces nothing in
+ * the reference (it consumes the raw layouts directly); once per scene. */
+int surf_scene_create(const surf_scene_inputs* in, void* stream, surf_scene** out);
+void surf_scene_destroy(surf_scene* s);
+int surf_scene_get_stats(const surf_scene* s, surf_scene_stats* out);
+/* finetune mode optimises volumes[l] in place (surf.py:43-44,72): refresh the padded copy */
+int surf_scene_update_volume(surf_scene* s, int32_t level, const float* d_volume, int64_t n_vox, void* stream);
+
+/* ---- network ----------------------------------------------------------------------------
+ * HOST pointers to an ImplicitSurface state_dict (names in SURVEY.md §5). */
+typedef struct surf_net_inputs {
+  /* SDFNetworkSparse (sdf_network.py:27-93) */
+  int32_t n_lin;                           /* 7 */
+  int32_t in_dim[SURF_SDF_LAYERS];         /* 27,156,156,156,156,156,156 */
+  int32_t out_dim[SURF_SDF_LAYERS];        /* 128,128,101,128,128,128,129 */
+  const float* h_weight_v[SURF_SDF_LAYERS];/* (out,in)  weight_v, or the plain weight if h_weight_g NULL */
+  const float* h_weight_g[SURF_SDF_LAYERS];/* (out,)    nullable */
+  const float* h_bias[SURF_SDF_LAYERS];    /* (out,) */
+  int32_t multires;                        /* 4 -> PE dim 27 (embedder.py:39-51) */
+  int32_t skip_layer;                      /* 3, or -1 */
+  int32_t feat_channels;                   /* 28 */
+  float scale;                             /* 1.0 */
+  /* BlendingNetwork (blending_network.py:27-67): weight (out,in) + bias per Linear */
+  const float* h_blend_w[11];              /* ray_dir_fc.0,.2 base_fc.0,.2 vis_fc.0,.2 vis_fc2.0,.2 rgb_fc.0,.2,.4 */
+  const float* h_blend_b[11];
+  float blend_s;                           /* anti-alias pooling scalar `s` */
+  int32_t d_feature;                       /* 16 */
+  /* SingleVarianceNetwork (variance_network.py:5-11) */
+  float variance;
+} surf_net_inputs;
+
+int surf_net_create(const surf_net_inputs* in, void* stream, surf_net** out);
+void surf_net_destroy(surf_net* n);
+
+/* ---- render configuration (confs/surf.conf: model.implicit_surface.render) ---------------- */
+typedef struct surf_render_cfg {
+  int32_t n_stages;                        /* 4 */
+  int32_t n_samples[SURF_MAX_STAGES];      /* 64,32,24,16 */
+  float sample_ranges[SURF_MAX_STAGES];    /* 1.0,0.4,0.1,0.01 */
+  int32_t n_depth;                         /* 256 probe depths */
+  int32_t perturb;                         /* jitter on/off (perturb > 0) */
+  float cos_anneal_ratio;                  /* 1.0 in validation */
+  int32_t chunk_rays;                      /* rays per reference render() call: the empty-mask fallback
+                                              (implicit_surface.py:88-89) is evaluated per chunk; 0 = all rays */
+  const float* d_lin_tables;               /* torch.linspace(0,1,n) for n = n_samples[0..], then n_depth,
+                                              concatenated (host-generated: linspace is not reproducible by
+                                              a device formula) */
+  int32_t mlp_mode;                        /* 0 = fp32 FFMA, 1 = tensor-core (reserved) */
+} surf_render_cfg;
+
+/* Outputs of render_core; any pointer may be NULL (not written).  Shapes use B rays, S samples,
+ * P = B*S.  Matches the inference keys of the dict built at implicit_surface.py:247-266. */
+typedef struct surf_render_outputs {
+  float* d_color_fine;        /* (B,3) */
+  float* d_render_depth;      /* (B,) */
+  float* d_sdf_depth;         /* (B,1) */
+  float* d_normal;            /* (B,3) rotated by inv(c2w0[:3,:3]) */
+  float* d_val_normal;        /* (B,3) sum g*w*inside_sphere, unrotated (validate(), :380-382) */
+  float* d_weights;           /* (B,S) */
+  float* d_weight_sum;        /* (B,1) */
+  float* d_weight_max;        /* (B,1) */
+  uint8_t* d_valid_mask;      /* (B,1) bool */
+  float* d_inside_sphere;     /* (B,S) */
+  float* d_mid_inside_sphere; /* (B,1) */
+  float* d_mid_z_vals;        /* (B,S) */
+  float* d_gradients;         /* (B,S,3)  REQUIRED */
+  float* d_sdf;               /* (P,1)    REQUIRED (tail of `sparse_sdf`) */
+  float* d_gradient_error_sums; /* (2,) [sum relax_inside*err, sum relax_inside]; accumulated (zero it first) */
+  /* stage outputs for parity tests (nullable) */
+  uint8_t* d_point_flags;     /* (P,) bit0 voxel mask, bit1 computed */
+  float* d_point_color;       /* (P,3) */
+  uint8_t* d_point_views;     /* (P,) bitmask of valid source views */
+  int32_t* d_prev_idx;        /* (B,) first zero-crossing index */
+  float* d_alpha;             /* (B,S) */
+} surf_render_outputs;
+
+size_t surf_render_workspace_bytes(int64_t n_rays, int32_t n_samples_total, int32_t n_src_views);
+
+/* ImplicitSurface.render lines 270-311: coarse-to-fine z sampling.  d_t_rand (B,n_stages) raw
+ * U[0,1) draws (the 0.5 shift is applied inside), NULL = no jitter.  Outputs sorted z_vals (B,S)
+ * and (optional) the expected surface depth (B,). */
+int surf_sample_rays(const surf_scene* s, const surf_render_cfg* cfg, const float* d_rays_o,
+                     const float* d_rays_d, const float* d_near, const float* d_far, const float* d_t_rand,
+                     int64_t n_rays, float* d_z_vals, float* d_surf_z, void* stream);
+
+/* ImplicitSurface.render_core (implicit_surface.py:64-266) for inference keys.  d_z_vals (B,S). */
+int surf_render_core(const surf_scene* s, const surf_net* n, const surf_render_cfg* cfg, const float* d_rays_o,
+                     const float* d_rays_d, const float* d_z_vals, int64_t n_rays, int32_t n_samples_total,
+                     const surf_render_outputs* out, void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* ImplicitSurface.render = sample_rays + render_core on one stream; z_vals kept in workspace. */
+int surf_render_rays(const surf_scene* s, const surf_net* n, const surf_render_cfg* cfg, const float* d_rays_o,
+                     const float* d_rays_d, const float* d_near, const float* d_far, const float* d_t_rand,
+                     int64_t n_rays, const surf_render_outputs* out, void* d_workspace, size_t workspace_bytes,
+                     void* stream);
+
+/* SDFNetworkSparse.sdf / .gradient (sdf_network.py:123-141) on a flat point list.
+ * d_sdf (n,) required; d_grad (n,3) nullable (forward only when NULL). */
+int surf_sdf_points(const surf_scene* s, const surf_net* n, const float* d_pts, int64_t n_pts, float* d_sdf,
+                    float* d_grad, void* stream);
+
+/* extract_geometry's SDF query (implicit_surface.py:337-351): u[x,y,z] = -sdf(xs[x],ys[y],zs[z]) on the
+ * tensor-product grid of the three coordinate tables (host torch.linspace, uploaded).  Dense (Q16).
+ * d_u is (nx,ny,nz) row-major.  sparsify != 0: opt-in fast mode, points whose 4-level voxel mask is 0
+ * get `fill` instead of an MLP evaluation (NOT result-identical outside the mask). */
+int surf_sdf_grid(const surf_scene* s, const surf_net* n, const float* d_xs, int32_t nx, const float* d_ys,
+                  int32_t ny, const float* d_zs, int32_t nz, float* d_u, int32_t sparsify, float fill,
+                  void* stream);
+
+/* ---- stage-isolated entry points (parity tests; same kernels/device functions) ------------ */
+/* lookup_volume(pts, mask_volumes, 'nearest').any(-1)  (projector.py:392-420, implicit_surface.py:86) */
+int surf_point_mask(const surf_scene* s, const float* d_pts, int64_t n_pts, uint8_t* d_mask, void* stream);
+/* lookup_sparse_volume (projector.py:377-390) -> (n, feat_ch*n_levels) */
+int surf_lookup_sparse(const surf_scene* s, const float* d_pts, int64_t n_pts, float* d_feats, void* stream);
+/* lookup_feature (projector.py:501-556) -> feat_views (n,V,19), ray_diff (n,V,4), mask (n,V) u8 */
+int surf_lookup_feature(const surf_scene* s, const float* d_pts, int64_t n_pts, float* d_feat_views,
+                        float* d_ray_diff, uint8_t* d_mask, void* stream);
+/* BlendingNetwork.forward (blending_network.py:69-117) on given inputs -> rgb (n,3) */
+int surf_blend(const surf_net* n, const float* d_feat_views, const float* d_ray_diff, const uint8_t* d_mask,
+               int64_t n_pts, int32_t n_src_views, float* d_rgb, void* stream);
+/* render_core lines 75-89: z_vals -> mid_z (B,S), flags (P,) with the per-chunk fallback applied */
+int surf_point_flags(const surf_scene* s, const surf_render_cfg* cfg, const float* d_rays_o, const float* d_rays_d,
+                     const float* d_z_vals, int64_t n_rays, int32_t n_samples_total, float* d_mid_z,
+                     uint8_t* d_flags, void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* ---- misc ------------------------------------------------------------------------------- */
+int surf_version(void);
+const char* surf_last_error(void);
+/* number of kernel launches issued by this library in this process (bench.py's gpu_launches) */
+int64_t surf_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SURF_B200_H */

@@ -1,0 +1,359 @@
+// K4: NeuS sigmoid-CDF alpha, transmittance scan, colour / depth / normal compositing and the first
+// SDF zero-crossing depth, one warp per ray (implicit_surface.py:122-216; quirks Q8-Q12), plus the
+// host-side orchestration of render_core / render_rays and the network handle.
+#include <math.h>
+#include <string.h>
+
+#include "surf_internal.cuh"
+
+int surf_build_sdf_weights(const surf_net_inputs* in, surf_net* net, cudaStream_t st,
+                           int (*dev_alloc)(surf_net*, void**, size_t));
+int surf_build_blend_weights(const surf_net_inputs* in, surf_net* net, cudaStream_t st,
+                             int (*dev_alloc)(surf_net*, void**, size_t));
+int surf_flags_pass(const surf_scene* s, const surf_render_cfg* cfg, const float* d_rays_o, const float* d_rays_d,
+                    const float* d_z_vals, int64_t B, int S, float* d_mid, uint8_t* d_flags, float* d_sdf,
+                    float* d_grad, int32_t* d_list, int32_t* d_counter, int32_t* d_chunk_any, int n_chunks,
+                    int chunk_rays, cudaStream_t st);
+
+#define COMP_WARPS 8
+#define COMP_MAXT 8   // up to 256 samples per ray
+
+__device__ __forceinline__ float sigmoid_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__global__ void __launch_bounds__(COMP_WARPS * 32)
+k_composite(const DevScene sc, int64_t B, int S, float sample_dist, float inv_s, float cos_anneal,
+            const float* __restrict__ rays_o, const float* __restrict__ rays_d, const float* __restrict__ z_vals,
+            const uint8_t* __restrict__ flags, const float* __restrict__ sdf, const float* __restrict__ grad,
+            const float* __restrict__ color, const uint8_t* __restrict__ views, const surf_render_outputs out) {
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  float gerr_num = 0.f, gerr_den = 0.f;
+  for (int64_t r = (int64_t)blockIdx.x * COMP_WARPS + wib; r < B; r += (int64_t)gridDim.x * COMP_WARPS) {
+    const float ox = rays_o[r * 3], oy = rays_o[r * 3 + 1], oz = rays_o[r * 3 + 2];
+    const float dx = rays_d[r * 3], dy = rays_d[r * 3 + 1], dz = rays_d[r * 3 + 2];
+    const int64_t p0 = r * S;
+    float carry = 1.0f;                       // running exclusive transmittance
+    float wsum = 0.f, wmax = -INFINITY, cr = 0.f, cg = 0.f, cb = 0.f, nx = 0.f, ny = 0.f, nz = 0.f;
+    float vx = 0.f, vy = 0.f, vz = 0.f, dsum = 0.f;
+    int nvalid = 0;
+    int first_cross = -1;
+    float score_any = 0.f;
+    const int T = (S + 31) >> 5;
+    for (int t = 0; t < T; ++t) {
+      const int j = t * 32 + lane;
+      const bool in = j < S;
+      float alpha = 0.f, mid = 0.f, gxv = 0.f, gyv = 0.f, gzv = 0.f, inside = 0.f, relax = 0.f, s_here = 100.f;
+      float vm = 0.f, col0 = 0.f, col1 = 0.f, col2 = 0.f;
+      bool cross = false;
+      if (in) {
+        const int64_t p = p0 + j;
+        const float z = z_vals[p];
+        const float dist = (j + 1 < S) ? __fsub_rn(z_vals[p + 1], z) : sample_dist;
+        mid = __fadd_rn(z, __fmul_rn(dist, 0.5f));
+        const uint8_t f = flags[p];
+        vm = (f & 1) ? 1.f : 0.f;
+        s_here = sdf[p];
+        gxv = grad[p * 3]; gyv = grad[p * 3 + 1]; gzv = grad[p * 3 + 2];
+        if (f & 2) {
+          col0 = color[p * 3]; col1 = color[p * 3 + 1]; col2 = color[p * 3 + 2];
+          if (__popc((unsigned)views[p]) > 1) nvalid++;
+        }
+        const float true_cos = dx * gxv + dy * gyv + dz * gzv;
+        float iter_cos = -(fmaxf(-true_cos * 0.5f + 0.5f, 0.f) * (1.0f - cos_anneal) + fmaxf(-true_cos, 0.f) * cos_anneal);
+        iter_cos *= vm;
+        const float step = fminf(fmaxf(iter_cos, -10.f), 10.f) * dist * 0.5f;
+        const float prev_cdf = sigmoid_acc((s_here - step) * inv_s);
+        const float next_cdf = sigmoid_acc((s_here + step) * inv_s);
+        alpha = fminf(fmaxf(((prev_cdf - next_cdf) + 1e-5f) / (prev_cdf + 1e-5f), 0.f), 1.f) * vm;
+        const float px = ray_at(ox, dx, mid), py = ray_at(oy, dy, mid), pz = ray_at(oz, dz, mid);
+        const float pn = sqrtf(px * px + py * py + pz * pz);
+        inside = (pn < 1.0f ? 1.f : 0.f) * vm;
+        relax = (pn < 1.2f ? 1.f : 0.f) * vm;
+        if (j + 1 < S) {
+          const float s_next = sdf[p + 1];
+          const bool both = (f & 1) && (flags[p + 1] & 1);
+          cross = both && (s_here * s_next <= 0.f);
+        }
+      }
+      // exclusive product scan of (1 - alpha + 1e-7) in sample order
+      const float fac = in ? (1.0f - alpha + 1e-7f) : 1.0f;
+      float incl = fac;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const float up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl *= up;
+      }
+      float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+      if (lane == 0) excl = 1.0f;
+      const float trans = carry * excl;
+      carry *= __shfl_sync(0xffffffffu, incl, 31);
+      const float w = alpha * trans;
+      if (in) {
+        const int64_t p = p0 + j;
+        if (out.d_weights) out.d_weights[p] = w;
+        if (out.d_inside_sphere) out.d_inside_sphere[p] = inside;
+        if (out.d_alpha) out.d_alpha[p] = alpha;
+        wsum += w;
+        wmax = fmaxf(wmax, w);
+        cr += col0 * w; cg += col1 * w; cb += col2 * w;
+        nx += gxv * w; ny += gyv * w; nz += gzv * w;
+        vx += gxv * w * inside; vy += gyv * w * inside; vz += gzv * w * inside;
+        dsum += mid * w;
+        const float gn = sqrtf(gxv * gxv + gyv * gyv + gzv * gzv) - 1.0f;
+        gerr_num += relax * gn * gn;
+        gerr_den += relax;
+      }
+      const unsigned cb_ = __ballot_sync(0xffffffffu, cross);
+      if (cb_ && first_cross < 0) first_cross = t * 32 + (__ffs(cb_) - 1);
+      if (cb_) score_any = 1.f;
+    }
+    wsum = warp_sum(wsum); wmax = warp_max(wmax);
+    cr = warp_sum(cr); cg = warp_sum(cg); cb = warp_sum(cb);
+    nx = warp_sum(nx); ny = warp_sum(ny); nz = warp_sum(nz);
+    vx = warp_sum(vx); vy = warp_sum(vy); vz = warp_sum(vz);
+    dsum = warp_sum(dsum);
+    int nv_total = nvalid;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nv_total += __shfl_xor_sync(0xffffffffu, nv_total, o);
+    if (lane == 0) {
+      const float* R = sc.rot0inv;
+      const float camz = R[6] * dx + R[7] * dy + R[8] * dz;
+      if (out.d_color_fine) { out.d_color_fine[r * 3] = cr; out.d_color_fine[r * 3 + 1] = cg; out.d_color_fine[r * 3 + 2] = cb; }
+      if (out.d_render_depth) out.d_render_depth[r] = dsum * camz;
+      if (out.d_normal) {
+        out.d_normal[r * 3] = R[0] * nx + R[1] * ny + R[2] * nz;
+        out.d_normal[r * 3 + 1] = R[3] * nx + R[4] * ny + R[5] * nz;
+        out.d_normal[r * 3 + 2] = R[6] * nx + R[7] * ny + R[8] * nz;
+      }
+      if (out.d_val_normal) { out.d_val_normal[r * 3] = vx; out.d_val_normal[r * 3 + 1] = vy; out.d_val_normal[r * 3 + 2] = vz; }
+      if (out.d_weight_sum) out.d_weight_sum[r] = wsum;
+      if (out.d_weight_max) out.d_weight_max[r] = wmax;
+      if (out.d_valid_mask) out.d_valid_mask[r] = nv_total > 8 ? 1 : 0;
+      // ---- first zero crossing (Q12) ----
+      const int i0 = first_cross < 0 ? 0 : first_cross;   // argmax of an all-zero row is 0
+      const int i1 = i0 + 1;
+      float sdf_depth = 0.f, mid_in = 0.f;
+      if (i1 < S) {
+        const int64_t a = p0 + i0, b = p0 + i1;
+        auto mid_of = [&](int j) {
+          const float z = z_vals[p0 + j];
+          const float dist = (j + 1 < S) ? __fsub_rn(z_vals[p0 + j + 1], z) : sample_dist;
+          return __fadd_rn(z, __fmul_rn(dist, 0.5f));
+        };
+        auto inside_of = [&](int j, float m) {
+          const float px = ray_at(ox, dx, m), py = ray_at(oy, dy, m), pz = ray_at(oz, dz, m);
+          return ((sqrtf(px * px + py * py + pz * pz) < 1.0f) && (flags[p0 + j] & 1)) ? 1.f : 0.f;
+        };
+        const float za = mid_of(i0), zb = mid_of(i1);
+        mid_in = (0.5f * (inside_of(i0, za) + inside_of(i1, zb)) > 0.5f) ? 1.f : 0.f;
+        mid_in *= score_any;
+        const float g1x = grad[a * 3], g1y = grad[a * 3 + 1], g1z = grad[a * 3 + 2];
+        const float g2x = grad[b * 3], g2y = grad[b * 3 + 1], g2z = grad[b * 3 + 2];
+        const float cosd = (g1x * g2x + g1y * g2y + g1z * g2z) /
+                           (sqrtf(g1x * g1x + g1y * g1y + g1z * g1z) * sqrtf(g2x * g2x + g2y * g2y + g2z * g2z) + 1e-8f);
+        mid_in *= (cosd > 0.5f) ? 1.f : 0.f;
+        const float s1 = sdf[a], s2 = sdf[b];
+        const float z0 = (s1 * zb - s2 * za) / (s1 - s2 + 1e-10f);
+        sdf_depth = z0 * camz * mid_in;
+      }
+      if (out.d_sdf_depth) out.d_sdf_depth[r] = sdf_depth;
+      if (out.d_mid_inside_sphere) out.d_mid_inside_sphere[r] = mid_in;
+      if (out.d_prev_idx) out.d_prev_idx[r] = i0;
+    }
+  }
+  if (out.d_gradient_error_sums) {
+    gerr_num = warp_sum(gerr_num);
+    gerr_den = warp_sum(gerr_den);
+    if (lane == 0 && gerr_den > 0.f) {
+      atomicAdd(out.d_gradient_error_sums, gerr_num);
+      atomicAdd(out.d_gradient_error_sums + 1, gerr_den);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// workspace layout
+// ---------------------------------------------------------------------------------------------
+struct Workspace {
+  float* z_vals;     // P
+  float* mid_z;      // P
+  uint8_t* flags;    // P
+  uint8_t* views;    // P
+  float* color;      // 3P
+  int32_t* list;     // P
+  float* feat;       // P * V * 20
+  float* rdiff;      // P * V * 4
+  int32_t* counter;  // 1 (+ pad)
+  int32_t* chunk_any;// n_chunks
+  size_t total;
+};
+
+static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static void carve(Workspace* w, void* base, int64_t B, int S, int V) {
+  const size_t P = (size_t)B * S;
+  size_t off = 0;
+  char* b = (char*)base;
+  auto take = [&](size_t bytes) {
+    void* p = b ? (void*)(b + off) : nullptr;
+    off += align_up(bytes);
+    return p;
+  };
+  w->z_vals = (float*)take(P * 4);
+  w->mid_z = (float*)take(P * 4);
+  w->flags = (uint8_t*)take(P);
+  w->views = (uint8_t*)take(P);
+  w->color = (float*)take(P * 12);
+  w->list = (int32_t*)take(P * 4);
+  w->feat = (float*)take(P * (size_t)(V > 0 ? V : 1) * 20 * 4);
+  w->rdiff = (float*)take(P * (size_t)(V > 0 ? V : 1) * 16);
+  w->counter = (int32_t*)take(256);
+  w->chunk_any = (int32_t*)take(((size_t)B + 1) * 4);
+  w->total = off;
+}
+
+extern "C" size_t surf_render_workspace_bytes(int64_t n_rays, int32_t n_samples_total, int32_t n_src_views) {
+  Workspace w;
+  carve(&w, nullptr, n_rays, n_samples_total, n_src_views);
+  return w.total;
+}
+
+static int render_core_impl(const surf_scene* s, const surf_net* n, const surf_render_cfg* cfg, const float* d_rays_o,
+                            const float* d_rays_d, const float* d_z_vals, int64_t B, int S,
+                            const surf_render_outputs* out, const Workspace& w, cudaStream_t st) {
+  SURF_CHECK_ARG(out->d_gradients && out->d_sdf, "outputs d_gradients and d_sdf are required");
+  SURF_CHECK_ARG((int64_t)B * S < 0x7fffffffll, "too many sample points for one call");
+  const int chunk_rays = (cfg->chunk_rays > 0 && cfg->chunk_rays < B) ? cfg->chunk_rays : (int)B;
+  const int n_chunks = (int)((B + chunk_rays - 1) / chunk_rays);
+  const int64_t P = B * S;
+  float* mid = out->d_mid_z_vals ? out->d_mid_z_vals : w.mid_z;
+  uint8_t* flags = out->d_point_flags ? out->d_point_flags : w.flags;
+  uint8_t* views = out->d_point_views ? out->d_point_views : w.views;
+  float* color = out->d_point_color ? out->d_point_color : w.color;
+  int rc = surf_flags_pass(s, cfg, d_rays_o, d_rays_d, d_z_vals, B, S, mid, flags, out->d_sdf, out->d_gradients,
+                           w.list, w.counter, w.chunk_any, n_chunks, chunk_rays, st);
+  if (rc) return rc;
+  PointSource src;
+  memset(&src, 0, sizeof(src));
+  src.mode = 1;
+  src.rays_o = d_rays_o;
+  src.rays_d = d_rays_d;
+  src.mid_z = mid;
+  src.S = S;
+  src.list = w.list;
+  src.count = w.counter;
+  src.n = P;
+  rc = launch_sdf_mlp(s, n, src, out->d_sdf, out->d_gradients, false, st);
+  if (rc) return rc;
+  if (s->dev.V > 0) {
+    rc = launch_lookup_feature(s, src, w.feat, w.rdiff, nullptr, false, st);
+    if (rc) return rc;
+    rc = launch_blend(s, n, w.feat, w.rdiff, nullptr, s->dev.V, false, w.list, w.counter, P, color, views, st);
+    if (rc) return rc;
+  }
+  const float sample_dist = 2.0f / (float)cfg->n_samples[0];
+  int64_t g = (B + COMP_WARPS - 1) / COMP_WARPS;
+  const int64_t cap = (int64_t)surf_num_sms() * 8;
+  k_composite<<<(int)(g < cap ? g : cap), COMP_WARPS * 32, 0, st>>>(s->dev, B, S, sample_dist, n->dev.inv_s,
+                                                                    cfg->cos_anneal_ratio, d_rays_o, d_rays_d, d_z_vals,
+                                                                    flags, out->d_sdf, out->d_gradients, color, views,
+                                                                    *out);
+  SURF_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int surf_render_core(const surf_scene* s, const surf_net* n, const surf_render_cfg* cfg,
+                                const float* d_rays_o, const float* d_rays_d, const float* d_z_vals, int64_t n_rays,
+                                int32_t n_samples_total, const surf_render_outputs* out, void* d_workspace,
+                                size_t workspace_bytes, void* stream) {
+  SURF_CHECK_ARG(s && n && cfg && d_rays_o && d_rays_d && d_z_vals && out && d_workspace, "null pointer");
+  if (n_rays <= 0) return 0;
+  Workspace w;
+  carve(&w, d_workspace, n_rays, n_samples_total, s->dev.V);
+  SURF_CHECK_ARG(workspace_bytes >= w.total, "workspace too small (surf_render_workspace_bytes)");
+  return render_core_impl(s, n, cfg, d_rays_o, d_rays_d, d_z_vals, n_rays, n_samples_total, out, w,
+                          (cudaStream_t)stream);
+}
+
+extern "C" int surf_render_rays(const surf_scene* s, const surf_net* n, const surf_render_cfg* cfg,
+                                const float* d_rays_o, const float* d_rays_d, const float* d_near, const float* d_far,
+                                const float* d_t_rand, int64_t n_rays, const surf_render_outputs* out,
+                                void* d_workspace, size_t workspace_bytes, void* stream) {
+  SURF_CHECK_ARG(s && n && cfg && d_rays_o && d_rays_d && d_near && d_far && out && d_workspace, "null pointer");
+  if (n_rays <= 0) return 0;
+  int S = 0;
+  for (int i = 0; i < cfg->n_stages && i < SURF_MAX_STAGES; ++i) S += cfg->n_samples[i];
+  Workspace w;
+  carve(&w, d_workspace, n_rays, S, s->dev.V);
+  SURF_CHECK_ARG(workspace_bytes >= w.total, "workspace too small (surf_render_workspace_bytes)");
+  int rc = surf_sample_rays(s, cfg, d_rays_o, d_rays_d, d_near, d_far, d_t_rand, n_rays, w.z_vals, nullptr, stream);
+  if (rc) return rc;
+  return render_core_impl(s, n, cfg, d_rays_o, d_rays_d, w.z_vals, n_rays, S, out, w, (cudaStream_t)stream);
+}
+
+extern "C" int surf_point_flags(const surf_scene* s, const surf_render_cfg* cfg, const float* d_rays_o,
+                                const float* d_rays_d, const float* d_z_vals, int64_t n_rays, int32_t n_samples_total,
+                                float* d_mid_z, uint8_t* d_flags, void* d_workspace, size_t workspace_bytes,
+                                void* stream) {
+  SURF_CHECK_ARG(s && cfg && d_rays_o && d_rays_d && d_z_vals && d_flags && d_workspace, "null pointer");
+  if (n_rays <= 0) return 0;
+  Workspace w;
+  carve(&w, d_workspace, n_rays, n_samples_total, s->dev.V);
+  SURF_CHECK_ARG(workspace_bytes >= w.total, "workspace too small (surf_render_workspace_bytes)");
+  const int chunk_rays = (cfg->chunk_rays > 0 && cfg->chunk_rays < n_rays) ? cfg->chunk_rays : (int)n_rays;
+  const int n_chunks = (int)((n_rays + chunk_rays - 1) / chunk_rays);
+  return surf_flags_pass(s, cfg, d_rays_o, d_rays_d, d_z_vals, n_rays, n_samples_total, d_mid_z, d_flags, nullptr,
+                         nullptr, w.list, w.counter, w.chunk_any, n_chunks, chunk_rays, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------------------------
+// network handle
+// ---------------------------------------------------------------------------------------------
+static int net_alloc(surf_net* n, void** p, size_t bytes) {
+  if (n->n_owned >= 16) {
+    surf_set_error("net: too many allocations");
+    return -2;
+  }
+  SURF_CUDA(cudaMalloc(p, bytes < 16 ? 16 : bytes));
+  n->owned[n->n_owned++] = *p;
+  return 0;
+}
+
+extern "C" void surf_net_destroy(surf_net* n) {
+  if (!n) return;
+  for (int i = 0; i < n->n_owned; ++i) cudaFree(n->owned[i]);
+  delete n;
+}
+
+extern "C" int surf_net_create(const surf_net_inputs* in, void* stream, surf_net** out) {
+  SURF_CHECK_ARG(in && out, "inputs/out null");
+  {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+      surf_set_error("no CUDA device: surf_b200 has no CPU fallback");
+      return e != cudaSuccess ? (int)e : -3;
+    }
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  surf_net* n = new surf_net();
+  memset(n, 0, sizeof(*n));
+  n->n_sm = surf_num_sms();
+  int rc = surf_build_sdf_weights(in, n, st, net_alloc);
+  if (rc == 0) rc = surf_build_blend_weights(in, n, st, net_alloc);
+  if (rc == 0) {
+    n->scratch_bytes = (size_t)n->n_sm * 6 * 16 * MLP_THREADS * sizeof(float4);
+    void* p = nullptr;
+    rc = net_alloc(n, &p, n->scratch_bytes);
+    n->scratch = (float*)p;
+  }
+  if (rc) {
+    surf_net_destroy(n);
+    return rc;
+  }
+  // Q9: inv_s = clip(exp(10 * variance), 1e-6, 1e6)   (variance_network.py:10, implicit_surface.py:126)
+  float inv_s = expf(in->variance * 10.0f);
+  inv_s = fminf(fmaxf(inv_s, 1e-6f), 1e6f);
+  n->dev.inv_s = inv_s;
+  *out = n;
+  return 0;
+}

@@ -1,0 +1,299 @@
+// K1: coarse-to-fine ray sampling (one warp per ray) and the surface-region sparsity mask.
+//   reference: ImplicitSurface.render lines 270-311 and render_core lines 75-89.
+// HBM-bound random-gather kernels: 256 trilinear probes of the matching volume per ray
+// (8 x 4 B taps each) and 4 one-bit nearest lookups per sample point.
+#include "surf_internal.cuh"
+
+#define SAMPLE_WARPS 8
+#define SAMPLE_MAXS 256
+
+struct SampleCfg {
+  int n_stages;
+  int n[SURF_MAX_STAGES];
+  int off[SURF_MAX_STAGES];      // offset of stage table inside lin tables
+  float ratio[SURF_MAX_STAGES];
+  int n_depth, off_depth;
+  int S;
+  int perturb;
+};
+
+// grid_sampler_3d 'bilinear', zeros padding, align_corners=False on the (M,M,M) matching volume.
+__device__ __forceinline__ float probe_trilinear(const float* __restrict__ vol, int M, float px, float py, float pz) {
+  const float ix = gs_unnorm(pz, M);   // W axis <- world z
+  const float iy = gs_unnorm(py, M);
+  const float iz = gs_unnorm(px, M);   // D axis <- world x
+  const float fx = floorf(ix), fy = floorf(iy), fz = floorf(iz);
+  const float tx = ix - fx, ty = iy - fy, tz = iz - fz;
+  // reject far-away points before the int conversion
+  if (!(fx >= -1.f && fx < (float)M && fy >= -1.f && fy < (float)M && fz >= -1.f && fz < (float)M)) return 0.f;
+  const int x0 = (int)fx, y0 = (int)fy, z0 = (int)fz;
+  float acc = 0.f;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const int xi = x0 + (c & 1), yi = y0 + ((c >> 1) & 1), zi = z0 + (c >> 2);
+    if (xi < 0 || xi >= M || yi < 0 || yi >= M || zi < 0 || zi >= M) continue;
+    const float w = ((c & 1) ? tx : 1.f - tx) * ((c & 2) ? ty : 1.f - ty) * ((c & 4) ? tz : 1.f - tz);
+    acc += __ldg(vol + ((size_t)zi * M + yi) * M + xi) * w;
+  }
+  return acc;
+}
+
+__global__ void __launch_bounds__(SAMPLE_WARPS * 32)
+k_sample_rays(const DevScene sc, const SampleCfg cfg, const float* __restrict__ lin, const float* __restrict__ rays_o,
+              const float* __restrict__ rays_d, const float* __restrict__ near, const float* __restrict__ far,
+              const float* __restrict__ t_rand, int64_t B, float* __restrict__ z_out, float* __restrict__ surf_out) {
+  __shared__ float zbuf[SAMPLE_WARPS][SAMPLE_MAXS];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  float* zs = zbuf[wib];
+  for (int64_t r = (int64_t)blockIdx.x * SAMPLE_WARPS + wib; r < B; r += (int64_t)gridDim.x * SAMPLE_WARPS) {
+    const float ox = rays_o[r * 3], oy = rays_o[r * 3 + 1], oz = rays_o[r * 3 + 2];
+    const float dx = rays_d[r * 3], dy = rays_d[r * 3 + 1], dz = rays_d[r * 3 + 2];
+    const float nr = near[r], fr = far[r];
+    const float span = __fsub_rn(fr, nr);
+    // ---- probe: softmax-expected depth over n_depth uniform samples (lines 283-291) ----
+    float m = -INFINITY, s = 0.f, t = 0.f;
+    for (int j = lane; j < cfg.n_depth; j += 32) {
+      const float z = __fadd_rn(nr, __fmul_rn(span, lin[cfg.off_depth + j]));
+      const float v = probe_trilinear(sc.matching, sc.mdim, ray_at(ox, dx, z), ray_at(oy, dy, z), ray_at(oz, dz, z));
+      const float mn = fmaxf(m, v);
+      const float c = expf(m - mn), e = expf(v - mn);
+      s = s * c + e;
+      t = t * c + e * z;
+      m = mn;
+    }
+    const float M = warp_max(m);
+    const float c = (m == -INFINITY) ? 0.f : expf(m - M);
+    s = warp_sum(s * c);
+    t = warp_sum(t * c);
+    const float surf = t / s;
+    if (surf_out && lane == 0) surf_out[r] = surf;
+    // ---- stage z values, exact op order of lines 271-277 / 293-306 ----
+    __syncwarp();
+    for (int st = 0; st < cfg.n_stages; ++st) {
+      const int n = cfg.n[st];
+      int base = 0;
+      for (int q = 0; q < st; ++q) base += cfg.n[q];
+      float lo, hi, shift = 0.f;
+      if (st == 0) {
+        lo = nr;
+        hi = fr;
+        if (cfg.perturb && t_rand) {
+          const float tr = __fsub_rn(t_rand[r * cfg.n_stages], 0.5f);
+          shift = __fdiv_rn(__fmul_rn(tr, 2.0f), (float)n);
+        }
+      } else {
+        const float w = __fmul_rn(span, cfg.ratio[st]);
+        lo = __fsub_rn(surf, w);
+        hi = __fadd_rn(surf, w);
+        if (hi > fr) lo = __fsub_rn(lo, __fsub_rn(hi, fr));
+        if (lo < nr) hi = __fadd_rn(hi, __fsub_rn(nr, lo));
+        lo = fminf(fmaxf(lo, nr), fr);
+        hi = fminf(fmaxf(hi, nr), fr);
+        if (cfg.perturb && t_rand) {
+          const float tr = __fsub_rn(t_rand[r * cfg.n_stages + st], 0.5f);
+          shift = __fdiv_rn(__fmul_rn(tr, __fsub_rn(hi, lo)), (float)n);
+        }
+      }
+      const float w = __fsub_rn(hi, lo);
+      const bool jit = cfg.perturb && t_rand;
+      for (int j = lane; j < n; j += 32) {
+        float z = __fadd_rn(lo, __fmul_rn(w, lin[cfg.off[st] + j]));
+        if (jit) z = __fadd_rn(z, shift);
+        zs[base + j] = z;
+      }
+    }
+    __syncwarp();
+    // ---- merge the sorted runs by rank (== torch.sort of the concatenation, line 311) ----
+    for (int e = lane; e < cfg.S; e += 32) {
+      int a = 0, base = 0;
+      while (e >= base + cfg.n[a]) base += cfg.n[a++];
+      const float v = zs[e];
+      int rank = e - base;
+      int bb = 0;
+      for (int b = 0; b < cfg.n_stages; ++b) {
+        const int nb = cfg.n[b];
+        if (b != a) {
+          // count elements of run b that precede v (ties: lower run id first)
+          int lo_i = 0, hi_i = nb;
+          while (lo_i < hi_i) {
+            const int mid = (lo_i + hi_i) >> 1;
+            const float u = zs[bb + mid];
+            const bool before = (b < a) ? (u <= v) : (u < v);
+            if (before) lo_i = mid + 1; else hi_i = mid;
+          }
+          rank += lo_i;
+        }
+        bb += nb;
+      }
+      z_out[r * cfg.S + rank] = v;
+    }
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// render_core lines 75-89: section mid-points, voxel mask, compaction of valid points.
+// One thread per sample point.  Also writes the masked-out defaults (Q7): sdf = 100, grad = 0.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_point_flags(const DevScene sc, const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+              const float* __restrict__ z_vals, int64_t B, int S, float sample_dist, int chunk_rays,
+              float* __restrict__ mid_out, uint8_t* __restrict__ flags, float* __restrict__ sdf_out,
+              float* __restrict__ grad_out, int32_t* __restrict__ list, int32_t* __restrict__ counter,
+              int32_t* __restrict__ chunk_any) {
+  const int64_t P = B * S;
+  const int lane = threadIdx.x & 31;
+  for (int64_t base = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) - lane; base < P;
+       base += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = base + lane;
+    bool valid = false;
+    if (p < P) {
+      const int64_t r = p / S;
+      const int j = (int)(p - r * S);
+      const float z = z_vals[p];
+      const float dist = (j + 1 < S) ? __fsub_rn(z_vals[p + 1], z) : sample_dist;
+      const float mid = __fadd_rn(z, __fmul_rn(dist, 0.5f));
+      const float px = ray_at(rays_o[r * 3], rays_d[r * 3], mid);
+      const float py = ray_at(rays_o[r * 3 + 1], rays_d[r * 3 + 1], mid);
+      const float pz = ray_at(rays_o[r * 3 + 2], rays_d[r * 3 + 2], mid);
+      valid = scene_point_mask(sc, px, py, pz);
+      if (mid_out) mid_out[p] = mid;
+      flags[p] = valid ? 3 : 0;          // bit0 voxel mask, bit1 computed
+      if (sdf_out) sdf_out[p] = 100.0f;
+      if (grad_out) {
+        grad_out[p * 3] = 0.f;
+        grad_out[p * 3 + 1] = 0.f;
+        grad_out[p * 3 + 2] = 0.f;
+      }
+      if (valid) chunk_any[r / chunk_rays] = 1;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, valid);
+    if (bal) {
+      int start = 0;
+      if (lane == 0) start = atomicAdd(counter, __popc(bal));
+      start = __shfl_sync(0xffffffffu, start, 0);
+      if (valid) list[start + __popc(bal & ((1u << lane) - 1))] = (int32_t)p;
+    }
+  }
+}
+
+// Q6: a chunk (= one reference render() call) without any valid point evaluates its first 10 points.
+__global__ void k_empty_chunk_fallback(int64_t B, int S, int chunk_rays, int n_chunks, uint8_t* __restrict__ flags,
+                                       int32_t* __restrict__ list, int32_t* __restrict__ counter,
+                                       const int32_t* __restrict__ chunk_any) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_chunks || chunk_any[c]) return;
+  const int64_t p0 = (int64_t)c * chunk_rays * S;
+  int64_t np = (int64_t)chunk_rays * S;
+  if (p0 + np > B * S) np = B * S - p0;
+  const int k = np < 10 ? (int)np : 10;
+  const int start = atomicAdd(counter, k);
+  for (int i = 0; i < k; ++i) {
+    flags[p0 + i] |= 2;
+    list[start + i] = (int32_t)(p0 + i);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// stage kernels
+// ---------------------------------------------------------------------------------------------
+__global__ void k_point_mask(const DevScene sc, const float* __restrict__ pts, int64_t n, uint8_t* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = scene_point_mask(sc, pts[i * 3], pts[i * 3 + 1], pts[i * 3 + 2]) ? 1 : 0;
+}
+
+__global__ void k_lookup_sparse(const DevScene sc, const float* __restrict__ pts, int64_t n, float* __restrict__ out) {
+  const int64_t total = n * sc.n_levels;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = i / sc.n_levels;
+    const int l = (int)(i - p * sc.n_levels);
+    float f[7];
+    sparse_level<0>(sc, l, pts[p * 3], pts[p * 3 + 1], pts[p * 3 + 2], nullptr, f);
+    float* o = out + p * (sc.n_levels * sc.feat_ch) + l * sc.feat_ch;
+    for (int c = 0; c < sc.feat_ch; ++c) o[c] = f[c];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static int make_sample_cfg(const surf_render_cfg* cfg, SampleCfg* sc) {
+  SURF_CHECK_ARG(cfg->n_stages >= 1 && cfg->n_stages <= SURF_MAX_STAGES, "n_stages");
+  int off = 0, S = 0;
+  sc->n_stages = cfg->n_stages;
+  for (int i = 0; i < SURF_MAX_STAGES; ++i) {
+    sc->n[i] = i < cfg->n_stages ? cfg->n_samples[i] : 0;
+    sc->ratio[i] = i < cfg->n_stages ? cfg->sample_ranges[i] : 0.f;
+    sc->off[i] = off;
+    off += sc->n[i];
+    S += sc->n[i];
+  }
+  sc->n_depth = cfg->n_depth;
+  sc->off_depth = off;
+  sc->S = S;
+  sc->perturb = cfg->perturb;
+  SURF_CHECK_ARG(S >= 1 && S <= SAMPLE_MAXS, "total samples per ray must be 1..256");
+  SURF_CHECK_ARG(cfg->n_depth >= 1, "n_depth");
+  return 0;
+}
+
+static int blocks_for(int64_t n, int per_block, int per_sm) {
+  int64_t g = (n + per_block - 1) / per_block;
+  const int64_t cap = (int64_t)surf_num_sms() * per_sm;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+extern "C" int surf_sample_rays(const surf_scene* s, const surf_render_cfg* cfg, const float* d_rays_o,
+                                const float* d_rays_d, const float* d_near, const float* d_far,
+                                const float* d_t_rand, int64_t n_rays, float* d_z_vals, float* d_surf_z,
+                                void* stream) {
+  SURF_CHECK_ARG(s && cfg && d_rays_o && d_rays_d && d_near && d_far && d_z_vals, "null pointer");
+  SURF_CHECK_ARG(s->dev.matching, "scene has no matching volume");
+  SURF_CHECK_ARG(cfg->d_lin_tables, "lin tables missing");
+  SampleCfg sc;
+  int rc = make_sample_cfg(cfg, &sc);
+  if (rc) return rc;
+  if (n_rays <= 0) return 0;
+  k_sample_rays<<<blocks_for(n_rays, SAMPLE_WARPS, 8), SAMPLE_WARPS * 32, 0, (cudaStream_t)stream>>>(
+      s->dev, sc, cfg->d_lin_tables, d_rays_o, d_rays_d, d_near, d_far, d_t_rand, n_rays, d_z_vals, d_surf_z);
+  SURF_LAUNCH_CHECK();
+  return 0;
+}
+
+// workspace layout helper shared with render.cu
+int surf_flags_pass(const surf_scene* s, const surf_render_cfg* cfg, const float* d_rays_o, const float* d_rays_d,
+                    const float* d_z_vals, int64_t B, int S, float* d_mid, uint8_t* d_flags, float* d_sdf,
+                    float* d_grad, int32_t* d_list, int32_t* d_counter, int32_t* d_chunk_any, int n_chunks,
+                    int chunk_rays, cudaStream_t st) {
+  SURF_CUDA(cudaMemsetAsync(d_counter, 0, sizeof(int32_t), st));
+  SURF_CUDA(cudaMemsetAsync(d_chunk_any, 0, sizeof(int32_t) * n_chunks, st));
+  const float sample_dist = 2.0f / (float)cfg->n_samples[0];
+  const int64_t P = B * S;
+  k_point_flags<<<blocks_for(P, 256, 8), 256, 0, st>>>(s->dev, d_rays_o, d_rays_d, d_z_vals, B, S, sample_dist,
+                                                       chunk_rays, d_mid, d_flags, d_sdf, d_grad, d_list, d_counter,
+                                                       d_chunk_any);
+  SURF_LAUNCH_CHECK();
+  k_empty_chunk_fallback<<<(n_chunks + 127) / 128, 128, 0, st>>>(B, S, chunk_rays, n_chunks, d_flags, d_list,
+                                                                 d_counter, d_chunk_any);
+  SURF_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int surf_point_mask(const surf_scene* s, const float* d_pts, int64_t n_pts, uint8_t* d_mask, void* stream) {
+  SURF_CHECK_ARG(s && d_pts && d_mask, "null pointer");
+  if (n_pts <= 0) return 0;
+  k_point_mask<<<blocks_for(n_pts, 256, 8), 256, 0, (cudaStream_t)stream>>>(s->dev, d_pts, n_pts, d_mask);
+  SURF_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int surf_lookup_sparse(const surf_scene* s, const float* d_pts, int64_t n_pts, float* d_feats, void* stream) {
+  SURF_CHECK_ARG(s && d_pts && d_feats, "null pointer");
+  if (n_pts <= 0) return 0;
+  k_lookup_sparse<<<blocks_for(n_pts * s->dev.n_levels, 256, 8), 256, 0, (cudaStream_t)stream>>>(s->dev, d_pts,
+                                                                                                 n_pts, d_feats);
+  SURF_LAUNCH_CHECK();
+  return 0;
+}

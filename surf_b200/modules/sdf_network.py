@@ -1,0 +1,137 @@
+"""SDFNetworkSparse — drop-in for models/modules/sdf_network.py:27-152.
+
+Same constructor arguments, same geometric initialisation, same parameter names
+(``lin{l}.weight_g / weight_v / bias``) so a reference checkpoint loads unchanged.  ``sdf`` and
+``gradient`` run the hand-written sm_100a kernel (csrc/sdf_mlp.cu) through the C-ABI; there is no
+PyTorch fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import _lib
+from ..scene import GLOBAL_SCENE_CACHE, PreparedScene
+from .embedder import embedder_out_dim
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class SDFNetworkSparse(nn.Module):
+    def __init__(self, d_in, d_out, d_hidden, n_layers, skip_in=(4,), multires=0, bias=0.5, scale=1,
+                 geometric_init=True, weight_norm=True, inside_outside=False, feat_channels=32, feat_multires=2):
+        super().__init__()
+        if feat_multires > 0:
+            raise NotImplementedError("feat_multires > 0 is not used by any shipped conf (confs/*.conf: 0)")
+        self.multires = int(multires)
+        self.d_in_raw = int(d_in)
+        d_in = embedder_out_dim(multires, d_in)
+        dims = [d_in] + [d_hidden + feat_channels for _ in range(n_layers)] + [d_out]
+        self.dims = dims
+        self.num_layers = len(dims)
+        self.skip_in = tuple(skip_in)
+        self.scale = float(scale)
+        self.feat_channels = int(feat_channels)
+        self.weight_norm = bool(weight_norm)
+        for l in range(0, self.num_layers - 1):
+            out_dim = dims[l + 1] - dims[0] if (l + 1) in self.skip_in else dims[l + 1]
+            if l < self.num_layers - 2:
+                out_dim = out_dim - feat_channels
+            lin = nn.Linear(dims[l], out_dim)
+            if geometric_init:      # sdf_network.py:62-86: SDF ~ ||x|| - bias at initialisation
+                if l == self.num_layers - 2:
+                    sign = -1.0 if inside_outside else 1.0
+                    torch.nn.init.normal_(lin.weight, mean=sign * np.sqrt(np.pi) / np.sqrt(dims[l]), std=0.0001)
+                    torch.nn.init.constant_(lin.bias, -sign * bias)
+                    torch.nn.init.constant_(lin.weight[:, -feat_channels:], 0.0)
+                    torch.nn.init.constant_(lin.bias[-feat_channels:], 0.0)
+                elif multires > 0 and l == 0:
+                    torch.nn.init.constant_(lin.bias, 0.0)
+                    torch.nn.init.constant_(lin.weight[:, 3:], 0.0)
+                    torch.nn.init.normal_(lin.weight[:, :3], 0.0, np.sqrt(2) / np.sqrt(out_dim))
+                elif multires > 0 and l in self.skip_in:
+                    torch.nn.init.constant_(lin.bias, 0.0)
+                    torch.nn.init.normal_(lin.weight, 0.0, np.sqrt(2) / np.sqrt(out_dim))
+                    torch.nn.init.constant_(lin.weight[:, -(dims[0] - 3 + feat_channels):], 0.0)
+                else:
+                    torch.nn.init.constant_(lin.bias, 0.0)
+                    torch.nn.init.normal_(lin.weight, 0.0, np.sqrt(2) / np.sqrt(out_dim))
+                    torch.nn.init.constant_(lin.weight[:, -feat_channels:], 0.0)
+            if weight_norm:
+                import warnings
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore")
+                    lin = nn.utils.weight_norm(lin)     # parameter names weight_g / weight_v, as the reference
+            setattr(self, "lin" + str(l), lin)
+        self._net_owner = None      # set by ImplicitSurface: the object that builds the surf_net handle
+
+    # -- C-ABI description of this network -----------------------------------------------------
+    def fill_net_inputs(self, inp: "_lib.NetInputs", keep: list):
+        n_lin = self.num_layers - 1
+        if n_lin != _lib.SDF_LAYERS:
+            raise NotImplementedError("the sm_100a SDF kernel is specialised for n_layers=6 (7 Linear layers)")
+        if len(self.skip_in) > 1:
+            raise NotImplementedError("at most one skip layer")
+        inp.n_lin = n_lin
+        inp.multires = self.multires
+        inp.skip_layer = self.skip_in[0] if self.skip_in else -1
+        inp.feat_channels = self.feat_channels
+        inp.scale = self.scale
+        for l in range(n_lin):
+            lin = getattr(self, "lin" + str(l))
+            if hasattr(lin, "weight_v"):
+                v = lin.weight_v.detach().float().cpu().contiguous()
+                g = lin.weight_g.detach().float().cpu().contiguous().reshape(-1)
+                keep += [v, g]
+                inp.h_weight_v[l], inp.h_weight_g[l] = v.data_ptr(), g.data_ptr()
+            else:
+                v = lin.weight.detach().float().cpu().contiguous()
+                keep.append(v)
+                inp.h_weight_v[l], inp.h_weight_g[l] = v.data_ptr(), None
+            b = lin.bias.detach().float().cpu().contiguous()
+            keep.append(b)
+            inp.h_bias[l] = b.data_ptr()
+            inp.out_dim[l], inp.in_dim[l] = int(v.shape[0]), int(v.shape[1])
+
+    def _handles(self, volumes, indexes):
+        if self._net_owner is None:
+            raise RuntimeError("SDFNetworkSparse must be owned by an ImplicitSurface to build its device weights")
+        net = self._net_owner().net_handle()
+        scene = volumes if isinstance(volumes, PreparedScene) else GLOBAL_SCENE_CACHE.get(volumes, indexes)
+        return scene, net
+
+    # -- reference API -------------------------------------------------------------------------
+    def sdf(self, x, volumes, indexes=None):
+        """(n,3) -> (n,1)   (sdf_network.py:123-124).  ``volumes`` may be a PreparedScene."""
+        scene, net = self._handles(volumes, indexes)
+        x = x.detach().to(torch.float32).contiguous()
+        out = torch.empty((x.shape[0], 1), dtype=torch.float32, device=x.device)
+        _lib.check(_lib.load().surf_sdf_points(scene.handle, net, x.data_ptr(), x.shape[0], out.data_ptr(), None,
+                                               _stream()), "sdf_points")
+        return out
+
+    def gradient(self, x, volumes, indexes=None, with_sdf=False):
+        """d sdf / d x (n,3) by the in-kernel analytic reverse pass (sdf_network.py:129-141).
+
+        The reference also returns the second-order ``smooth`` term (:143-150), a training-only extra
+         that is not implemented; zeros are returned in its place."""
+        scene, net = self._handles(volumes, indexes)
+        x = x.detach().to(torch.float32).contiguous()
+        sdf = torch.empty((x.shape[0], 1), dtype=torch.float32, device=x.device)
+        grad = torch.empty((x.shape[0], 3), dtype=torch.float32, device=x.device)
+        _lib.check(_lib.load().surf_sdf_points(scene.handle, net, x.data_ptr(), x.shape[0], sdf.data_ptr(),
+                                               grad.data_ptr(), _stream()), "sdf_points(grad)")
+        if with_sdf:
+            return sdf, grad
+        return grad, torch.zeros_like(grad)
+
+    def forward(self, inputs, volumes, indexes=None):
+        """The reference returns (n, d_out) = [sdf, 128 hidden features]; the hidden features are dead
+        on the render path (implicit_surface.py:95-97 scatters them and never reads them), so the kernel
+        evaluates only row 0 of lin6.  Returns (n,1)."""
+        return self.sdf(inputs, volumes, indexes)

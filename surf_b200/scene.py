@@ -1,0 +1,189 @@
+"""scene_prepare: wraps the reference-layout scene tensors into a ``surf_scene`` handle.
+
+The reference hands raw tensors to every ``render()`` call (implicit_surface.py:268); the B200 path
+converts them ONCE per scene into the compact HBM layout (int32 index tables, 1-bit masks, 32-byte
+voxel rows, NHWC feature maps — DESIGN.md §3) and caches the handle keyed on the identity of the
+input tensors, so the drop-in signatures stay unchanged.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from collections import OrderedDict
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    return t.detach().to(torch.float32).contiguous()
+
+
+class PreparedScene:
+    """Owns a ``surf_scene*``.  Lists in renderer order (fine->coarse / high->low res)."""
+
+    def __init__(self, volumes: Sequence[torch.Tensor], sparse_idxes: Sequence[torch.Tensor],
+                 mask_volumes: Optional[Sequence[torch.Tensor]] = None,
+                 matching_volume: Optional[torch.Tensor] = None, imgs: Optional[torch.Tensor] = None,
+                 features: Optional[Sequence[torch.Tensor]] = None, intrs: Optional[torch.Tensor] = None,
+                 c2ws: Optional[torch.Tensor] = None):
+        lib = _lib.load()
+        if isinstance(volumes, torch.Tensor):
+            volumes, sparse_idxes = [volumes], [sparse_idxes]
+            if mask_volumes is not None and isinstance(mask_volumes, torch.Tensor):
+                mask_volumes = [mask_volumes]
+        dev = volumes[0].device
+        if dev.type != "cuda":
+            raise RuntimeError("surf_b200: scene tensors must live on a CUDA device (no CPU fallback)")
+        self.device = dev
+        n_levels = len(volumes)
+        if not (1 <= n_levels <= _lib.MAX_LEVELS):
+            raise ValueError("1..4 volume levels supported")
+        keep = []
+        inp = _lib.SceneInputs()
+        inp.n_levels = n_levels
+        inp.feat_ch = int(volumes[0].shape[1])
+        for l in range(n_levels):
+            v = _f32c(volumes[l])
+            idx = sparse_idxes[l].detach()
+            if idx.dtype != torch.int64:
+                idx = idx.to(torch.int64)
+            idx = idx.contiguous()
+            if not (idx.dim() == 3 and idx.shape[0] == idx.shape[1] == idx.shape[2]):
+                raise ValueError("sparse index tables must be cubic (N,N,N) (projector.py:324 assumes it)")
+            keep += [v, idx]
+            inp.dim[l] = int(idx.shape[0])
+            inp.n_vox[l] = int(v.shape[0])
+            inp.d_volumes[l] = v.data_ptr() if v.numel() else None
+            inp.d_sparse_idx[l] = idx.data_ptr()
+            if mask_volumes is not None:
+                m = _f32c(mask_volumes[l])
+                if m.numel() != idx.numel():
+                    raise ValueError("mask volume %d does not match its index table" % l)
+                keep.append(m)
+                inp.d_mask_volumes[l] = m.data_ptr()
+        if matching_volume is not None:
+            mv = _f32c(matching_volume)
+            keep.append(mv)
+            inp.d_matching_volume = mv.data_ptr()
+            inp.match_dim = int(mv.shape[-1])
+            if not (mv.shape[-1] == mv.shape[-2] == mv.shape[-3]):
+                raise ValueError("matching volume must be cubic")
+        self.n_views = 0
+        if imgs is not None:
+            im = _f32c(imgs)
+            keep.append(im)
+            nv, _, H, W = im.shape
+            if len(features) != 4:
+                raise ValueError("4 feature pyramid levels expected (high-res -> low-res)")
+            inp.n_views, inp.img_h, inp.img_w, inp.n_feat_levels = nv, H, W, 4
+            inp.d_imgs = im.data_ptr()
+            for i, f in enumerate(features):
+                f = _f32c(f)
+                if tuple(f.shape) != (nv, 4, H >> i, W >> i):
+                    raise ValueError("feature level %d has shape %s, expected %s" % (i, tuple(f.shape), (nv, 4, H >> i, W >> i)))
+                keep.append(f)
+                inp.d_features[i] = f.data_ptr()
+            self.n_views = nv
+        if c2ws is not None:
+            # host-side, with the reference's own routine (torch.inverse, projector.py:529)
+            c2w_h = c2ws.detach().to(torch.float32).cpu().contiguous()
+            w2c_h = torch.inverse(c2w_h).contiguous()
+            K_h = intrs.detach().to(torch.float32).cpu().contiguous()
+            keep += [c2w_h, w2c_h, K_h]
+            inp.h_c2ws, inp.h_w2cs, inp.h_intrs = c2w_h.data_ptr(), w2c_h.data_ptr(), K_h.data_ptr()
+            if imgs is None:
+                inp.n_views = int(c2w_h.shape[0])
+                self.n_views = inp.n_views
+        elif imgs is not None:
+            raise ValueError("imgs given without camera matrices")
+        self.n_levels = n_levels
+        self.n_src_views = max(0, self.n_views - 1)
+        self.has_matching = matching_volume is not None
+        self.has_images = imgs is not None
+        handle = C.c_void_p()
+        with torch.cuda.device(dev):
+            _lib.check(lib.surf_scene_create(C.byref(inp), _stream(), C.byref(handle)), "scene_create")
+            # conversion kernels read the inputs asynchronously: finish before `keep` may be freed
+            torch.cuda.current_stream().synchronize()
+        self._h = handle
+        self._lib = lib
+        del keep
+
+    @property
+    def handle(self):
+        if self._h is None:
+            raise RuntimeError("scene already destroyed")
+        return self._h
+
+    def stats(self):
+        st = _lib.SceneStats()
+        _lib.check(self._lib.surf_scene_get_stats(self.handle, C.byref(st)), "scene_get_stats")
+        return {"bytes_index": st.bytes_index, "bytes_volumes": st.bytes_volumes, "bytes_masks": st.bytes_masks,
+                "bytes_matching": st.bytes_matching, "bytes_images": st.bytes_images,
+                "n_vox": [int(st.n_vox[i]) for i in range(self.n_levels)]}
+
+    def update_volume(self, level: int, volume: torch.Tensor):
+        v = _f32c(volume)
+        _lib.check(self._lib.surf_scene_update_volume(self.handle, level, v.data_ptr(), v.shape[0], _stream()),
+                   "scene_update_volume")
+        torch.cuda.current_stream().synchronize()
+
+    def destroy(self):
+        if getattr(self, "_h", None) is not None:
+            self._lib.surf_scene_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
+class SceneCache:
+    """Small LRU of PreparedScene keyed on the identity + version of the raw tensors."""
+
+    def __init__(self, capacity=4):
+        self.capacity = capacity
+        self._d = OrderedDict()
+
+    @staticmethod
+    def _key(tensors):
+        k = []
+        for t in tensors:
+            if t is None:
+                k.append(None)
+            else:
+                k.append((t.data_ptr(), tuple(t.shape), t._version, str(t.device)))
+        return tuple(k)
+
+    def get(self, volumes, sparse_idxes, mask_volumes=None, matching_volume=None, imgs=None, features=None,
+            intrs=None, c2ws=None) -> PreparedScene:
+        as_list = lambda x: [] if x is None else ([x] if isinstance(x, torch.Tensor) else list(x))
+        flat = as_list(volumes) + as_list(sparse_idxes) + as_list(mask_volumes) + [matching_volume, imgs] \
+            + as_list(features) + [intrs, c2ws]
+        key = self._key(flat)
+        hit = self._d.get(key)
+        if hit is not None:
+            self._d.move_to_end(key)
+            return hit
+        sc = PreparedScene(volumes, sparse_idxes, mask_volumes, matching_volume, imgs, features, intrs, c2ws)
+        self._d[key] = sc
+        while len(self._d) > self.capacity:
+            _, old = self._d.popitem(last=False)
+            old.destroy()
+        return sc
+
+    def clear(self):
+        for sc in self._d.values():
+            sc.destroy()
+        self._d.clear()
+
+
+GLOBAL_SCENE_CACHE = SceneCache()

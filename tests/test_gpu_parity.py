@@ -1,0 +1,327 @@
+"""Parity of the CUDA path (through the C-ABI, via the module mirror) against the CPU oracle and the
+reference-generated golden vectors.
+
+Bars (BASELINE.json north_star): bit-exact for sample indices / sparsity masks in stage-isolated mode
+(oracle floats in); fp32 outputs within 1e-4 relative (scale-relative, helpers.assert_close).
+End-to-end integer outputs use a mismatch census: reductions (softmax / 4x4 inverses / K=4 matmuls)
+cannot be made order-identical to MKL, so a sample within an ulp of a voxel or pixel boundary may flip;
+every mismatch must be explained by such a boundary and the count must stay tiny.
+"""
+import numpy as np
+import pytest
+import torch
+
+import surf_oracle as O
+from helpers import RTOL_FP32, assert_close, assert_equal_int, load_golden, scene_from_recipe
+from surf_b200 import conf, synthetic
+from surf_b200.modules import projector as P
+from surf_b200.modules.implicit_surface import ImplicitSurface
+
+pytestmark = pytest.mark.gpu
+
+RENDER_CASES = ["render_v2_perturbed", "render_v2_init", "render_v4_perturbed", "render_miss"]
+DEV = "cuda:0"
+
+
+def build(g):
+    m = ImplicitSurface(conf.default_implicit_surface_conf())
+    m.load_state_dict(g["sd"], strict=True)
+    return m.to(DEV)
+
+
+def gpu_scene(m, sc):
+    d = sc.to(DEV)
+    return d, m.prepare(d.matching_volume, d.volumes, d.sparse_idxes, d.mask_volumes, d.imgs, d.features, d.intrs,
+                        d.c2ws)
+
+
+def oracle_render(g, sc, stages=True, t_rand=None, pts_random=None):
+    net = O.OracleNet(g["sd"])
+    i = g["in"]
+    torch.manual_seed(int(g["recipe"]["torch_seed"]))
+    return net, O.render(net, i["rays_o"], i["rays_d"], i["near"], i["far"], sc.matching_volume, sc.volumes,
+                         sc.sparse_idxes, sc.mask_volumes, sc.imgs, sc.features, sc.intrs, sc.c2ws, 1.0,
+                         t_rand=t_rand, pts_random=pts_random, return_stages=stages)
+
+
+# ------------------------------------------------------------------------------------------------
+# stage-isolated: masks and gathers
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", RENDER_CASES[:3])
+def test_voxel_mask_bit_exact(name):
+    g = load_golden(name)
+    sc = scene_from_recipe(g["recipe"])
+    m = build(g)
+    _, ps = gpu_scene(m, sc)
+    _, ref = oracle_render(g, sc)
+    gen = torch.Generator().manual_seed(5)
+    extra = torch.rand(200000, 3, generator=gen) * 2.4 - 1.2          # incl. points outside the cube
+    # points exactly on voxel boundaries of the finest level (round-half-even cases)
+    N = sc.mask_volumes[0].shape[-1]
+    edges = (torch.randint(0, 2 * N + 1, (20000, 3), generator=gen).float() / N) - 1.0
+    pts = torch.cat([ref["_pts"], extra, edges])
+    want = O.point_mask(pts, sc.mask_volumes)
+    got = P.lookup_volume(pts.to(DEV), ps)[:, 0] > 0
+    assert_equal_int(got, want, "voxel mask")
+    assert 0.02 < float(want.float().mean()) < 0.98
+
+
+@pytest.mark.parametrize("name", RENDER_CASES[:3])
+def test_sparse_gather(name):
+    g = load_golden(name)
+    sc = scene_from_recipe(g["recipe"])
+    m = build(g)
+    _, ps = gpu_scene(m, sc)
+    pv = torch.from_numpy(g["out"]["_pts_valid"])
+    got = P.lookup_sparse_volume(pv.to(DEV), ps)
+    assert_close(got, g["out"]["_sparse_feats"], 1e-5, "sparse feats vs reference golden")
+    gen = torch.Generator().manual_seed(6)
+    wild = torch.rand(50000, 3, generator=gen) * 3.0 - 1.5
+    assert_close(P.lookup_sparse_volume(wild.to(DEV), ps), O.lookup_sparse(wild, sc.volumes, sc.sparse_idxes), 1e-5,
+                 "sparse feats, extrapolating points")
+
+
+@pytest.mark.parametrize("name", RENDER_CASES[:3])
+def test_lookup_feature(name):
+    g = load_golden(name)
+    sc = scene_from_recipe(g["recipe"])
+    m = build(g)
+    _, ps = gpu_scene(m, sc)
+    pv = torch.from_numpy(g["out"]["_pts_valid"])
+    fv, rd, mk = P.lookup_feature(pv.to(DEV), ps)
+    ref_mask = torch.from_numpy(g["out"]["_view_mask"])
+    mism = (mk.cpu() != ref_mask)
+    # census: the projection uses MKL batched matmuls in the reference; a mismatch is only legal for
+    # a projection within 1e-3 px of an image border
+    assert int(mism.sum()) <= max(2, int(1e-4 * mism.numel())), "view-mask mismatches: %d" % int(mism.sum())
+    assert_close(rd, g["out"]["_ray_diff"], 1e-5, "ray_diff")
+    ok = ~mism.any(dim=1)
+    assert_close(fv.cpu()[ok], torch.from_numpy(g["out"]["_feat_views"])[ok], RTOL_FP32, "feat_views")
+
+
+@pytest.mark.parametrize("name", RENDER_CASES[:3])
+def test_blend(name):
+    g = load_golden(name)
+    m = build(g)
+    o = g["out"]
+    fv, rd, mk = (torch.from_numpy(o[k]).to(DEV) for k in ("_feat_views", "_ray_diff", "_view_mask"))
+    got = m.color_network(fv, rd, mk)
+    assert_close(got, o["_blend_rgb"], RTOL_FP32, "blend rgb vs reference golden")
+    # all views masked -> uniform softmax over the raw samples
+    mk0 = torch.zeros_like(mk)
+    net = O.OracleNet(g["sd"])
+    want = O.blend(net, fv.cpu(), rd.cpu(), mk0.cpu())
+    assert_close(m.color_network(fv, rd, mk0), want, RTOL_FP32, "blend rgb, nothing visible")
+
+
+# ------------------------------------------------------------------------------------------------
+# SDF MLP
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", RENDER_CASES[:3])
+def test_sdf_and_gradient(name):
+    g = load_golden(name)
+    sc = scene_from_recipe(g["recipe"])
+    m = build(g)
+    _, ps = gpu_scene(m, sc)
+    pv = torch.from_numpy(g["out"]["_pts_valid"]).to(DEV)
+    sdf = m.sdf_network.sdf(pv, ps)
+    assert_close(sdf, g["out"]["_sdf_full"][:, :1], RTOL_FP32, "sdf vs reference golden")
+    s2, grad = m.sdf_network.gradient(pv, ps, with_sdf=True)
+    assert_close(s2, g["out"]["_sdf_full"][:, :1], RTOL_FP32, "sdf (gradient kernel)")
+    assert_close(grad, g["out"]["_grad_valid"], RTOL_FP32, "d sdf / d x vs reference autograd")
+    assert torch.equal(sdf, s2), "forward-only and forward+reverse kernels must agree bit-for-bit"
+
+
+def test_sdf_wild_points_and_ragged_sizes():
+    g = load_golden("sdf_grid_24")
+    sc = scene_from_recipe(g["recipe"])
+    m = build(g)
+    _, ps = gpu_scene(m, sc)
+    wild = g["in"]["wild_pts"].to(DEV)
+    s, gr = m.sdf_network.gradient(wild, ps, with_sdf=True)
+    assert_close(s, g["out"]["wild_full"][:, :1], RTOL_FP32, "sdf, out-of-range points")
+    assert_close(gr, g["out"]["wild_grad"], RTOL_FP32, "gradient, out-of-range points")
+    # ragged / tiny / empty inputs
+    for n in (0, 1, 127, 128, 129, 323):
+        p = wild[:n]
+        out = m.sdf_network.sdf(p, ps)
+        assert out.shape == (n, 1)
+        if n:
+            assert torch.equal(out, s[:n])
+
+
+def test_sdf_grid_matches_reference_and_slabs():
+    g = load_golden("sdf_grid_24")
+    sc = scene_from_recipe(g["recipe"])
+    m = build(g)
+    _, ps = gpu_scene(m, sc)
+    res = int(g["recipe"]["resolution"])
+    u = m.sdf_grid(ps, [-1, -1, -1], [1, 1, 1], res)
+    assert_close(u, g["out"]["u"], RTOL_FP32, "u grid vs reference golden")
+    slabs = torch.cat([m.sdf_grid(ps, [-1, -1, -1], [1, 1, 1], res, x_range=(a, b)) for a, b in ((0, 7), (7, 8), (8, 24))])
+    assert torch.equal(slabs, u), "x-slab sharding must reproduce the full grid bit-for-bit"
+    # opt-in sparsified mode: identical inside the mask, constant outside (Q16)
+    us = m.sdf_grid(ps, [-1, -1, -1], [1, 1, 1], res, sparsify=True, fill=-100.0)
+    lin = torch.linspace(-1, 1, res)
+    xx, yy, zz = torch.meshgrid(lin, lin, lin, indexing="ij")
+    inside = O.point_mask(torch.stack([xx, yy, zz], -1).reshape(-1, 3), sc.mask_volumes).reshape(res, res, res)
+    assert torch.equal(us.cpu()[inside], u.cpu()[inside])
+    assert bool((us.cpu()[~inside] == -100.0).all())
+
+
+# ------------------------------------------------------------------------------------------------
+# sampler
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", RENDER_CASES)
+def test_sample_z(name):
+    g = load_golden(name)
+    sc = scene_from_recipe(g["recipe"])
+    m = build(g)
+    d, ps = gpu_scene(m, sc)
+    i = g["in"]
+    torch.manual_seed(int(g["recipe"]["torch_seed"]))
+    t_rand = O.draw_t_rand(i["rays_o"].shape[0], 4)
+    net = O.OracleNet(g["sd"])
+    z_ref, surf_ref = O.sample_z(net, i["rays_o"], i["rays_d"], i["near"], i["far"], sc.matching_volume, t_rand)
+    z, surf = m.sample_z(ps, i["rays_o"].to(DEV), i["rays_d"].to(DEV), i["near"].to(DEV), i["far"].to(DEV), t_rand)
+    z = z.cpu()
+    assert bool((z[:, 1:] >= z[:, :-1]).all()), "z_vals must be sorted"
+    assert_close(surf, surf_ref[:, 0], 1e-5, "expected surface depth")
+    assert float((z - z_ref).abs().max()) <= 4e-6, "z_vals differ by more than a few ulp"
+    # stage 0 does not depend on the probe: those 64 values must be present bit-exactly
+    lin = torch.linspace(0.0, 1.0, 64)
+    z0 = i["near"] + (i["far"] - i["near"]) * lin[None] + (t_rand[:, 0:1] - 0.5) * 2.0 / 64
+    for r in range(z.shape[0]):
+        assert np.isin(z0[r].numpy(), z[r].numpy()).all()
+    # no jitter path
+    z_nj, _ = m.sample_z(ps, i["rays_o"].to(DEV), i["rays_d"].to(DEV), i["near"].to(DEV), i["far"].to(DEV), None)
+    z_nj_ref, _ = O.sample_z(net, i["rays_o"], i["rays_d"], i["near"], i["far"], sc.matching_volume, None)
+    assert float((z_nj.cpu() - z_nj_ref).abs().max()) <= 4e-6
+
+
+# ------------------------------------------------------------------------------------------------
+# render_core, stage-isolated: the oracle's z_vals go in, integers must be bit-exact
+# ------------------------------------------------------------------------------------------------
+INT_KEYS = ["valid_mask", "inside_sphere", "mid_inside_sphere"]
+FLOAT_KEYS = ["color_fine", "render_depth", "sdf_depth", "normal", "gradients", "weights", "weight_sum",
+              "weight_max", "sparse_sdf", "gradient_error", "mid_z_vals", "s_val"]
+
+
+@pytest.mark.parametrize("name", RENDER_CASES)
+def test_render_core_stage_isolated(name):
+    g = load_golden(name)
+    sc = scene_from_recipe(g["recipe"])
+    m = build(g)
+    d, ps = gpu_scene(m, sc)
+    net, ref0 = oracle_render(g, sc)
+    z_vals = ref0["_z_vals"]                       # the oracle's own sorted z_vals go into both paths
+    i = g["in"]
+    pts_random = torch.rand(1024, 3, generator=torch.Generator().manual_seed(9)) * 2 - 1
+    ref = O.render_core(net, i["rays_o"], i["rays_d"], z_vals, sc.volumes, sc.sparse_idxes, sc.mask_volumes,
+                        sc.features, sc.imgs, sc.intrs, sc.c2ws, 1.0, pts_random=pts_random, return_stages=True)
+    out = m.render_core(i["rays_o"].to(DEV), i["rays_d"].to(DEV), z_vals.to(DEV), 2.0 / 64, ps,
+                        None, None, None, None, None, None, None, None, None, 1.0, None, pts_random=pts_random,
+                        return_stages=True)
+    flags = out["_point_flags"].cpu()
+    assert_equal_int(flags & 1, ref["_voxel_mask"], "voxel mask (stage-isolated)")
+    assert_equal_int((flags >> 1) & 1, ref["_compute_mask"], "computed-point mask incl. empty-chunk fallback")
+    assert np.array_equal(out["mid_z_vals"].cpu().numpy(), ref["mid_z_vals"].numpy()), "mid_z must be bit-identical"
+    vm = ref["_view_mask"]
+    bits = out["_point_views"].cpu()
+    got_vm = torch.stack([(bits >> v) & 1 for v in range(vm.shape[1])], dim=1).bool()
+    cm = ref["_compute_mask"]
+    mism = int((got_vm[cm] != vm[cm]).sum())
+    assert mism <= max(2, int(1e-4 * vm[cm].numel())), "view mask mismatches %d" % mism
+    if mism == 0:
+        for k in INT_KEYS:
+            assert_equal_int(out[k], ref[k], k)
+        assert_equal_int(out["_prev_idx"], ref["_prev_idx"][:, 0], "first zero-crossing index")
+    assert_close(out["_alpha"], ref["_alpha"], 5e-4, "alpha", floor=1.0)
+    for k in FLOAT_KEYS:
+        assert_close(out[k], ref[k], RTOL_FP32 if k not in ("weights", "weight_max") else 5e-4, k)
+
+
+# ------------------------------------------------------------------------------------------------
+# end to end against the reference golden
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", RENDER_CASES)
+def test_render_end_to_end_vs_reference(name):
+    g = load_golden(name)
+    sc = scene_from_recipe(g["recipe"])
+    m = build(g)
+    d, ps = gpu_scene(m, sc)
+    i = g["in"]
+    torch.manual_seed(int(g["recipe"]["torch_seed"]))          # same global-RNG stream as the reference run
+    out = m.render(i["rays_o"].to(DEV), i["rays_d"].to(DEV), i["near"].to(DEV), i["far"].to(DEV), d.matching_volume,
+                   d.volumes, d.sparse_idxes, d.mask_volumes, d.imgs, d.features, d.features, d.intrs, d.c2ws, 1.0,
+                   None, return_stages=True)
+    ref = g["out"]
+    vm_ref = torch.from_numpy(ref["_voxel_mask"])
+    vm = (out["_point_flags"].cpu() & 1).bool()
+    census = int((vm != vm_ref).sum())
+    assert census <= max(2, int(2e-4 * vm.numel())), "voxel-mask census: %d mismatches" % census
+    assert float((out["mid_z_vals"].cpu() - torch.from_numpy(ref["mid_z_vals"])).abs().max()) <= 4e-6
+    if census == 0:
+        for k in INT_KEYS:
+            assert_equal_int(out[k], ref[k], k)
+        for k in ["color_fine", "render_depth", "sdf_depth", "normal", "weight_sum", "gradient_error", "sparse_sdf"]:
+            assert_close(out[k], ref[k], 5e-4, k, floor=1e-2)
+        assert_close(out["gradients"], ref["gradients"], RTOL_FP32, "gradients")
+    assert set(out.keys()) >= {"color_fine", "render_depth", "sdf_depth", "normal", "valid_mask", "sparse_sdf",
+                               "mid_z_vals", "gradients", "s_val", "weights", "weight_sum", "weight_max",
+                               "gradient_error", "inside_sphere", "mid_inside_sphere"}
+
+
+def test_validate_image_vs_reference():
+    g = load_golden("validate_24x32")
+    sc = scene_from_recipe(g["recipe"])
+    m = build(g)
+    d, ps = gpu_scene(m, sc)
+    i = g["in"]
+    r = int(g["recipe"]["res_level"])
+    hw = (sc.H // r, sc.W // r)
+    torch.manual_seed(int(g["recipe"]["torch_seed"]))
+    out = m.validate(i["rays_o"].to(DEV), i["rays_d"].to(DEV), i["near"].to(DEV), i["far"].to(DEV), d.matching_volume,
+                     d.volumes, d.sparse_idxes, d.mask_volumes, d.imgs, d.features, d.features, d.intrs, d.c2ws,
+                     torch.tensor([-1.0, -1, -1]), torch.tensor([1.0, 1, 1]), hw, 1.0, None, extract_geometry=False)
+    assert isinstance(out["color_fine"], torch.Tensor) and out["color_fine"].device.type == "cpu"
+    assert isinstance(out["img_fine"], np.ndarray) and out["img_fine"].shape == (hw[0], hw[1], 3)
+    bad_rays = 0
+    for k in ["color_fine", "img_fine", "normal_img", "sdf_depth", "render_depth"]:
+        a = torch.as_tensor(np.asarray(out[k])).double().reshape(hw[0] * hw[1], -1)
+        b = torch.as_tensor(np.asarray(g["out"][k])).double().reshape(hw[0] * hw[1], -1)
+        scale = float(b.abs().max())
+        bad = ((a - b).abs() > 5e-4 * max(scale, 1e-2)).any(dim=1)
+        bad_rays = max(bad_rays, int(bad.sum()))
+    # a ray may differ only if one of its samples flipped a voxel-mask bit (ulp-level z difference)
+    assert bad_rays <= max(2, int(0.005 * hw[0] * hw[1])), "%d rays differ from the reference image" % bad_rays
+
+
+# ------------------------------------------------------------------------------------------------
+# size-independent properties on a larger scene
+# ------------------------------------------------------------------------------------------------
+def test_properties_larger_scene():
+    sc = synthetic.make_scene(3, 144, 200, 16, seed=4)
+    g = load_golden("render_v2_perturbed")
+    m = build(g)
+    d, ps = gpu_scene(m, sc)
+    o, dd, hw = synthetic.image_rays(sc, 2)            # 72 x 100 = 7200 rays, 29 chunks (last one ragged)
+    o, dd = o.to(DEV), dd.to(DEV)
+    near, far = d.near, d.far
+    torch.manual_seed(11)
+    t_rand = m.draw_chunk_randoms(o.shape[0])
+    full = m.render_image(ps, o, dd, near, far, t_rand=t_rand)
+    again = m.render_image(ps, o, dd, near, far, t_rand=t_rand)
+    for k in full:
+        assert torch.equal(full[k], again[k]), "render must be deterministic (%s)" % k
+    # ray sharding on chunk boundaries == whole image, bit for bit (the multi-GPU contract)
+    cut = 256 * 13
+    m.ray_batch = 256 * 4
+    a = m.render_image(ps, o[:cut], dd[:cut], near, far, t_rand=t_rand[:cut])
+    b = m.render_image(ps, o[cut:], dd[cut:], near, far, t_rand=t_rand[cut:])
+    for k in full:
+        assert torch.equal(torch.cat([a[k], b[k]]), full[k]), "sharded render differs (%s)" % k
+    assert bool(torch.isfinite(full["color_fine"]).all())
+    c = full["color_fine"]
+    assert float(c.min()) >= -1e-5 and float(c.max()) <= 1.0 + 1e-4      # convex blend of images in [0,1)
+    assert float((full["sdf_depth"] > 0).float().mean()) > 0.05            # rays do hit the r=0.5 sphere
