@@ -203,6 +203,14 @@ int surf_version(void);
 const char* surf_last_error(void);
 /* number of kernel launches issued by this library in this process (bench.py's gpu_launches) */
 int64_t surf_launch_count(void);
+/* Optional per-kernel device timing for bench.py's roofline: when enabled, every launch of the
+ * kernel classes below is bracketed by cudaEvents on its own stream.  surf_timing_read synchronises
+ * the recorded events, returns the summed duration (ms) and launch count per class since the last
+ * read, and resets.  kind: 0 = SDF MLP (fwd+grad), 1 = SDF MLP (fwd only), 2 = projection gather,
+ * 3 = blending MLP, 4 = sampler, 5 = point flags/mask, 6 = compositing. */
+#define SURF_TIMING_KINDS 7
+int surf_timing_enable(int32_t on);
+int surf_timing_read(double* ms_out /*[SURF_TIMING_KINDS]*/, int64_t* launches_out /*[SURF_TIMING_KINDS]*/);
 
 #ifdef __cplusplus
 }

@@ -138,6 +138,24 @@ def sparse_trilinear(volume: torch.Tensor, index: torch.Tensor, pts_zyx: torch.T
     return out
 
 
+def voxel_face_distance(pts: torch.Tensor, indexes: Sequence[torch.Tensor]) -> torch.Tensor:
+    """min over levels and axes of |c - round(c)| / ulp(c) for the sparse-grid coordinate c = (p+1)/voxel
+    (projector.py:231-242).  The trilinear feature lookup is continuous across voxel faces but its
+    GRADIENT is not: a point within rounding noise of a face (c is an exact integer in fp32 for about
+    4e-6 of all points per axis and level) gets a different d sdf / d x when its position changes by one
+    ulp.  Test helper: marks samples whose gradient the reference itself does not define robustly."""
+    p = pts.flip(-1)
+    dist = torch.full((pts.shape[0],), float("inf"))
+    for idx in indexes:
+        n = idx.shape[0]
+        voxel = torch.tensor(2.0) / (torch.tensor(float(n)) - 1)
+        c = (p + 1.0) / voxel
+        # in units of the fp32 spacing at c, so that "< 1.5" means "within rounding noise of a face"
+        ulp = torch.finfo(torch.float32).eps * c.abs().clamp(min=1.0)
+        dist = torch.minimum(dist, ((c - torch.round(c)).abs() / ulp).min(dim=1)[0])
+    return dist
+
+
 def lookup_sparse(pts: torch.Tensor, volumes: Sequence[torch.Tensor], indexes: Sequence[torch.Tensor]):
     """(n,3) -> (n, 7*levels); levels concatenated in the order given (fine->coarse) (:377-390)."""
     p = pts.flip(-1)
@@ -299,6 +317,29 @@ def ray_direction_diff(pts, ref_c2w, src_c2ws):
     return torch.cat([direction, dot], dim=-1).permute(1, 0, 2).contiguous()
 
 
+def projection_border_distance(pts, intrs, c2ws, features):
+    """min over source views and pyramid levels of the distance (in that level's pixels) between a
+    point's projection and the nearest image border / the w=0 plane (in camera units).  The per-view
+    validity mask (projector.py:536) flips across those borders, so a point closer than rounding noise
+    to one of them has no well-defined mask (e.g. every ray of pixel row 0 projects to y=0 in a source
+    view that differs from the reference only by an x offset).  Test helper."""
+    src_K, src_c2w = intrs[1:], c2ws[1:]
+    n = pts.shape[0]
+    homog = torch.cat([pts.t().contiguous(), torch.ones(1, n)], dim=0)
+    cam = torch.matmul(torch.inverse(src_c2w), homog[None])[:, :3]
+    dist = torch.full((n,), float("inf"))
+    for i, feat in enumerate(features):
+        K = src_K.clone()
+        K[:, :2] = K[:, :2] * (0.5 ** i)
+        h, w = feat.shape[-2:]
+        uvw = torch.matmul(K[:, :3, :3], cam)
+        xy = uvw[:, :2] / uvw[:, 2:]
+        d = torch.stack([xy[:, 0].abs(), (xy[:, 0] - w).abs(), xy[:, 1].abs(), (xy[:, 1] - h).abs(),
+                         uvw[:, 2].abs()], dim=0).min(dim=0)[0]          # (V,n)
+        dist = torch.minimum(dist, d.min(dim=0)[0])
+    return dist
+
+
 def lookup_feature(pts, imgs, intrs, c2ws, features):
     """-> feat_views (n,V,19) = [rgb3, f0(4), f1(4), f2(4), f3(4)], ray_diff (n,V,4), mask (n,V) bool."""
     src_K, src_c2w, ref_c2w = intrs[1:], c2ws[1:], c2ws[0]
@@ -341,7 +382,10 @@ def _seq(x, cw, name, idxs, final_act=True):
     return x
 
 
-def blend(net: OracleNet, feat_views, ray_diff, mask):
+def blend(net: OracleNet, feat_views, ray_diff, mask, e_ulp=None):
+    """``e_ulp`` (n,V) in {-1,0,+1}: test-only knob that moves the pooling exponentials by that many fp32
+    ulps, used by tests/helpers.blend_envelope to measure how ill-conditioned the reference's
+    anti-alias weights are at a point (they subtract nearly equal exponentials)."""
     cw = net.color
     m = mask[:, :, None].to(feat_views.dtype)
     V = feat_views.shape[1]
@@ -349,6 +393,11 @@ def blend(net: OracleNet, feat_views, ray_diff, mask):
     x = feat_views + _seq(ray_diff, cw, "ray_dir_fc", (0, 2))
     dot = ray_diff[..., 3:4]
     e = torch.exp(torch.abs(cw["s"]) * (dot - 1))
+    if e_ulp is not None:
+        up = torch.nextafter(e, torch.full_like(e, 4.0))
+        dn = torch.nextafter(e, torch.full_like(e, -4.0))
+        sh = e_ulp[:, :, None]
+        e = torch.where(sh > 0, up, torch.where(sh < 0, dn, e))
     wgt = (e - torch.min(e, dim=1, keepdim=True)[0]) * m
     wgt = wgt / (torch.sum(wgt, dim=1, keepdim=True) + 1e-8)
     mean = torch.sum(x * wgt, dim=1, keepdim=True)

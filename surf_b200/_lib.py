@@ -19,7 +19,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libsurf_b200.so")
 
 EXPORTS = [
-    "surf_version", "surf_last_error", "surf_launch_count",
+    "surf_version", "surf_last_error", "surf_launch_count", "surf_timing_enable", "surf_timing_read",
     "surf_scene_create", "surf_scene_destroy", "surf_scene_get_stats", "surf_scene_update_volume",
     "surf_net_create", "surf_net_destroy",
     "surf_render_workspace_bytes", "surf_sample_rays", "surf_render_core", "surf_render_rays",
@@ -117,6 +117,10 @@ def _declare(lib):
     lib.surf_last_error.argtypes = []
     lib.surf_launch_count.restype = i64
     lib.surf_launch_count.argtypes = []
+    lib.surf_timing_enable.restype = C.c_int
+    lib.surf_timing_enable.argtypes = [i32]
+    lib.surf_timing_read.restype = C.c_int
+    lib.surf_timing_read.argtypes = [P(C.c_double), P(i64)]
     lib.surf_scene_create.restype = C.c_int
     lib.surf_scene_create.argtypes = [P(SceneInputs), vp, P(vp)]
     lib.surf_scene_destroy.restype = None
@@ -185,3 +189,18 @@ def check(rc, what):
 
 def launch_count() -> int:
     return int(load().surf_launch_count())
+
+
+TIMING_KINDS = ["sdf_mlp_grad", "sdf_mlp_fwd", "lookup_feature", "blend", "sample_rays", "point_flags", "composite"]
+
+
+def timing_enable(on=True):
+    check(load().surf_timing_enable(1 if on else 0), "timing_enable")
+
+
+def timing_read():
+    """-> {kind: (ms_total, launches)} since the last read (synchronises the recorded events)."""
+    ms = (C.c_double * len(TIMING_KINDS))()
+    n = (C.c_int64 * len(TIMING_KINDS))()
+    check(load().surf_timing_read(ms, n), "timing_read")
+    return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(TIMING_KINDS)}

@@ -263,16 +263,25 @@ k_blend(const float* __restrict__ blob, float s_abs, const float* __restrict__ f
       s_m[r] = rec[19];
     }
     __syncthreads();
-    // ---- anti-alias pooling weights per point (blending_network.py:76-80) ----
+    // ---- anti-alias pooling weights (blending_network.py:76-80) ----
+    // weight = (e_v - min_v e_v) * mask / (sum + 1e-8) with e_v = exp(|s| (dot_v - 1)): a difference of
+    // nearly equal exponentials.  The reference's result is quantised to fp32 ulps of e_v, so e_v is
+    // formed here as the correctly rounded fp32 exponential (fp64 exp, rounded once) of the identically
+    // rounded fp32 argument: that keeps this path within the reference's own 1-ulp envelope.
+    if (tid < BL_ROWS) {
+      const float arg = __fmul_rn(s_abs, __fsub_rn(RD[3 * BAS + tid], 1.0f));
+      s_logit[tid] = (float)exp((double)arg);     // s_logit doubles as scratch for e_v until the last layer
+    }
+    __syncthreads();
     if (tid < ppt) {
       const int r0 = tid * V;
       float emin = INFINITY;
-      for (int v = 0; v < V; ++v) emin = fminf(emin, expf(s_abs * (RD[3 * BAS + r0 + v] - 1.0f)));
+      for (int v = 0; v < V; ++v) emin = fminf(emin, s_logit[r0 + v]);
       float wsum = 0.f;
-      for (int v = 0; v < V; ++v) wsum += (expf(s_abs * (RD[3 * BAS + r0 + v] - 1.0f)) - emin) * s_m[r0 + v];
-      const float winv = 1.0f / (wsum + 1e-8f);
+      for (int v = 0; v < V; ++v) wsum = __fadd_rn(wsum, __fmul_rn(__fsub_rn(s_logit[r0 + v], emin), s_m[r0 + v]));
+      const float den = __fadd_rn(wsum, 1e-8f);
       for (int v = 0; v < V; ++v)
-        s_wv[r0 + v] = (expf(s_abs * (RD[3 * BAS + r0 + v] - 1.0f)) - emin) * s_m[r0 + v] * winv;
+        s_wv[r0 + v] = __fdiv_rn(__fmul_rn(__fsub_rn(s_logit[r0 + v], emin), s_m[r0 + v]), den);
     }
     // ---- ray_dir_fc: 4 -> 16 -> 19, ELU; x = feat + dir (kept in XB rows 38..56) ----
     {
@@ -509,8 +518,10 @@ int launch_lookup_feature(const surf_scene* s, const PointSource& src, float* d_
                           uint8_t* d_mask, bool packed19, cudaStream_t st) {
   SURF_CHECK_ARG(s->dev.img0, "scene has no images / feature maps");
   if (src.n <= 0 || s->dev.V <= 0) return 0;
+  surf_time_begin(2, st);
   k_lookup_feature<<<cap_blocks(src.n * s->dev.V, 256, 8), 256, 0, st>>>(s->dev, src, d_feat, d_raydiff, d_mask,
                                                                          packed19 ? 1 : 0);
+  surf_time_end(2, st);
   SURF_LAUNCH_CHECK();
   return 0;
 }
@@ -529,8 +540,10 @@ int launch_blend(const surf_scene*, const surf_net* n, const float* d_feat, cons
   const int ppt = BL_ROWS / V;
   int64_t tiles = (n_pts + ppt - 1) / ppt;
   const int grid = (int)(tiles < n->n_sm ? tiles : n->n_sm);
+  surf_time_begin(3, st);
   k_blend<<<grid, BL_THREADS, smem, st>>>(n->dev.blend, n->dev.blend_s, d_feat, d_raydiff, d_mask, V,
                                           packed19 ? 1 : 0, list, count, n_pts, d_rgb, d_views);
+  surf_time_end(3, st);
   SURF_LAUNCH_CHECK();
   return 0;
 }

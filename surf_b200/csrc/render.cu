@@ -253,10 +253,12 @@ static int render_core_impl(const surf_scene* s, const surf_net* n, const surf_r
   const float sample_dist = 2.0f / (float)cfg->n_samples[0];
   int64_t g = (B + COMP_WARPS - 1) / COMP_WARPS;
   const int64_t cap = (int64_t)surf_num_sms() * 8;
+  surf_time_begin(6, st);
   k_composite<<<(int)(g < cap ? g : cap), COMP_WARPS * 32, 0, st>>>(s->dev, B, S, sample_dist, n->dev.inv_s,
                                                                     cfg->cos_anneal_ratio, d_rays_o, d_rays_d, d_z_vals,
                                                                     flags, out->d_sdf, out->d_gradients, color, views,
                                                                     *out);
+  surf_time_end(6, st);
   SURF_LAUNCH_CHECK();
   return 0;
 }

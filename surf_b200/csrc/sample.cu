@@ -256,8 +256,10 @@ extern "C" int surf_sample_rays(const surf_scene* s, const surf_render_cfg* cfg,
   int rc = make_sample_cfg(cfg, &sc);
   if (rc) return rc;
   if (n_rays <= 0) return 0;
+  surf_time_begin(4, (cudaStream_t)stream);
   k_sample_rays<<<blocks_for(n_rays, SAMPLE_WARPS, 8), SAMPLE_WARPS * 32, 0, (cudaStream_t)stream>>>(
       s->dev, sc, cfg->d_lin_tables, d_rays_o, d_rays_d, d_near, d_far, d_t_rand, n_rays, d_z_vals, d_surf_z);
+  surf_time_end(4, (cudaStream_t)stream);
   SURF_LAUNCH_CHECK();
   return 0;
 }
@@ -271,9 +273,11 @@ int surf_flags_pass(const surf_scene* s, const surf_render_cfg* cfg, const float
   SURF_CUDA(cudaMemsetAsync(d_chunk_any, 0, sizeof(int32_t) * n_chunks, st));
   const float sample_dist = 2.0f / (float)cfg->n_samples[0];
   const int64_t P = B * S;
+  surf_time_begin(5, st);
   k_point_flags<<<blocks_for(P, 256, 8), 256, 0, st>>>(s->dev, d_rays_o, d_rays_d, d_z_vals, B, S, sample_dist,
                                                        chunk_rays, d_mid, d_flags, d_sdf, d_grad, d_list, d_counter,
                                                        d_chunk_any);
+  surf_time_end(5, st);
   SURF_LAUNCH_CHECK();
   k_empty_chunk_fallback<<<(n_chunks + 127) / 128, 128, 0, st>>>(B, S, chunk_rays, n_chunks, d_flags, d_list,
                                                                  d_counter, d_chunk_any);

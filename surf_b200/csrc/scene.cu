@@ -31,6 +31,54 @@ int surf_num_sms() {
   return n;
 }
 
+// ---- optional kernel timing -------------------------------------------------------------------
+#include <mutex>
+#include <vector>
+struct TimedLaunch { int kind; cudaEvent_t a, b; };
+static bool g_timing = false;
+static std::mutex g_timing_mu;
+static std::vector<TimedLaunch> g_timed;
+static thread_local cudaEvent_t g_pending_begin = nullptr;
+
+void surf_time_begin(int kind, cudaStream_t st) {
+  if (!g_timing) return;
+  cudaEvent_t a;
+  if (cudaEventCreate(&a) != cudaSuccess) return;
+  cudaEventRecord(a, st);
+  g_pending_begin = a;
+}
+void surf_time_end(int kind, cudaStream_t st) {
+  if (!g_timing || !g_pending_begin) return;
+  cudaEvent_t b;
+  if (cudaEventCreate(&b) != cudaSuccess) return;
+  cudaEventRecord(b, st);
+  std::lock_guard<std::mutex> lk(g_timing_mu);
+  g_timed.push_back({kind, g_pending_begin, b});
+  g_pending_begin = nullptr;
+}
+extern "C" int surf_timing_enable(int32_t on) {
+  std::lock_guard<std::mutex> lk(g_timing_mu);
+  g_timing = on != 0;
+  return 0;
+}
+extern "C" int surf_timing_read(double* ms_out, int64_t* launches_out) {
+  SURF_CHECK_ARG(ms_out && launches_out, "null pointer");
+  std::lock_guard<std::mutex> lk(g_timing_mu);
+  for (int k = 0; k < SURF_TIMING_KINDS; ++k) { ms_out[k] = 0.0; launches_out[k] = 0; }
+  for (auto& t : g_timed) {
+    float ms = 0.f;
+    cudaEventSynchronize(t.b);
+    if (cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess && t.kind >= 0 && t.kind < SURF_TIMING_KINDS) {
+      ms_out[t.kind] += ms;
+      launches_out[t.kind] += 1;
+    }
+    cudaEventDestroy(t.a);
+    cudaEventDestroy(t.b);
+  }
+  g_timed.clear();
+  return 0;
+}
+
 extern "C" int surf_version(void) { return SURF_ABI_VERSION; }
 extern "C" const char* surf_last_error(void) { return g_err; }
 extern "C" int64_t surf_launch_count(void) { return (int64_t)g_launches.load(); }

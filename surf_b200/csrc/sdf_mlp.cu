@@ -567,17 +567,20 @@ int launch_sdf_mlp(const surf_scene* s, const surf_net* n, const PointSource& sr
   if (src.n <= 0) return 0;
   int64_t tiles = (src.n + MLP_TILE - 1) / MLP_TILE;
   int grid = (int)(tiles < n->n_sm ? tiles : n->n_sm);
+  surf_time_begin(d_grad ? 0 : 1, st);
   if (d_grad) {
     k_sdf_mlp<true><<<grid, MLP_THREADS, smem, st>>>(s->dev, n->dev, src, d_sdf, d_grad, n->scratch, negate ? 1 : 0);
   } else {
     k_sdf_mlp<false><<<grid, MLP_THREADS, smem, st>>>(s->dev, n->dev, src, d_sdf, nullptr, n->scratch, negate ? 1 : 0);
   }
+  surf_time_end(d_grad ? 0 : 1, st);
   SURF_LAUNCH_CHECK();
   return 0;
 }
 
 extern "C" int surf_sdf_points(const surf_scene* s, const surf_net* n, const float* d_pts, int64_t n_pts,
                                float* d_sdf, float* d_grad, void* stream) {
+  if (n_pts <= 0) return 0;
   SURF_CHECK_ARG(s && n && d_pts && d_sdf, "null pointer");
   SURF_CHECK_ARG(n_pts < 0x7fffffffll, "too many points for one call");
   PointSource src;

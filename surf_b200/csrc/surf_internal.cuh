@@ -87,6 +87,9 @@ struct surf_net {
 // error handling / launch accounting
 // ---------------------------------------------------------------------------------------------
 void surf_set_error(const char* fmt, ...);
+// bench-only kernel timing (scene.cu): RAII-less begin/end pair around a launch
+void surf_time_begin(int kind, cudaStream_t st);
+void surf_time_end(int kind, cudaStream_t st);
 void surf_count_launch(int n = 1);
 int surf_num_sms();
 

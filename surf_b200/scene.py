@@ -8,6 +8,7 @@ input tensors, so the drop-in signatures stay unchanged.
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from collections import OrderedDict
 from typing import Optional, Sequence
 
@@ -147,41 +148,46 @@ class PreparedScene:
 
 
 class SceneCache:
-    """Small LRU of PreparedScene keyed on the identity + version of the raw tensors."""
+    """Small LRU of PreparedScene keyed on the identity of the raw tensors.
+
+    An entry is only valid while every input tensor object is still alive (weak references) and
+    unmodified (``_version``): a freed tensor's address can be reused by the caching allocator, so
+    ``data_ptr`` alone would alias different scenes."""
 
     def __init__(self, capacity=4):
         self.capacity = capacity
         self._d = OrderedDict()
 
     @staticmethod
-    def _key(tensors):
-        k = []
-        for t in tensors:
-            if t is None:
-                k.append(None)
-            else:
-                k.append((t.data_ptr(), tuple(t.shape), t._version, str(t.device)))
-        return tuple(k)
+    def _flatten(volumes, sparse_idxes, mask_volumes, matching_volume, imgs, features, intrs, c2ws):
+        as_list = lambda x: [] if x is None else ([x] if isinstance(x, torch.Tensor) else list(x))
+        return as_list(volumes) + as_list(sparse_idxes) + as_list(mask_volumes) + [matching_volume, imgs] \
+            + as_list(features) + [intrs, c2ws]
 
     def get(self, volumes, sparse_idxes, mask_volumes=None, matching_volume=None, imgs=None, features=None,
             intrs=None, c2ws=None) -> PreparedScene:
-        as_list = lambda x: [] if x is None else ([x] if isinstance(x, torch.Tensor) else list(x))
-        flat = as_list(volumes) + as_list(sparse_idxes) + as_list(mask_volumes) + [matching_volume, imgs] \
-            + as_list(features) + [intrs, c2ws]
-        key = self._key(flat)
+        flat = self._flatten(volumes, sparse_idxes, mask_volumes, matching_volume, imgs, features, intrs, c2ws)
+        key = tuple(None if t is None else id(t) for t in flat)
         hit = self._d.get(key)
         if hit is not None:
-            self._d.move_to_end(key)
-            return hit
+            refs, versions, sc = hit
+            alive = all((r is None and t is None) or (r is not None and r() is t) for r, t in zip(refs, flat))
+            if alive and versions == tuple(None if t is None else t._version for t in flat):
+                self._d.move_to_end(key)
+                return sc
+            sc.destroy()
+            del self._d[key]
         sc = PreparedScene(volumes, sparse_idxes, mask_volumes, matching_volume, imgs, features, intrs, c2ws)
-        self._d[key] = sc
+        refs = tuple(None if t is None else weakref.ref(t) for t in flat)
+        versions = tuple(None if t is None else t._version for t in flat)
+        self._d[key] = (refs, versions, sc)
         while len(self._d) > self.capacity:
-            _, old = self._d.popitem(last=False)
+            _, (_, _, old) = self._d.popitem(last=False)
             old.destroy()
         return sc
 
     def clear(self):
-        for sc in self._d.values():
+        for _, _, sc in self._d.values():
             sc.destroy()
         self._d.clear()
 

@@ -72,3 +72,30 @@ def assert_equal_int(a, b, what=""):
     assert a.shape == b.shape, "%s: shape %s vs %s" % (what, tuple(a.shape), tuple(b.shape))
     ne = (a.to(torch.int64) != b.to(torch.int64))
     assert not bool(ne.any()), "%s: %d/%d integer mismatches" % (what, int(ne.sum()), b.numel())
+
+
+def blend_envelope(O, net, fv, rd, mk, n_random=4, seed=0):
+    """Conditioning envelope of the reference's anti-alias pooling weights.
+
+    weight = (exp(s (dot_v - 1)) - min_v exp(...)) / (sum + 1e-8) subtracts nearly equal fp32 exponentials
+    (blending_network.py:76-80).  With 3+ source views of similar viewing angle a ONE-ulp change of one
+    exponential moves the output by up to 0.2 in RGB (measured on the 5-view golden case), and torch's own
+    CPU exp is not correctly rounded (differs from the correctly rounded value in ~2 % of arguments), so
+    no independent implementation can match the reference bit-for-bit there.  Returns (reference output,
+    per-point envelope) where the envelope is the largest change of the oracle's output when the
+    exponentials move by +-1 ulp (each view alone, both signs, plus random patterns)."""
+    g = torch.Generator().manual_seed(seed)
+    base = O.blend(net, fv, rd, mk)
+    n, V = fv.shape[0], fv.shape[1]
+    env = torch.zeros(n)
+    pats = []
+    for v in range(V):
+        for sgn in (-1, 1):
+            p = torch.zeros(n, V, dtype=torch.int64)
+            p[:, v] = sgn
+            pats.append(p)
+    for _ in range(n_random):
+        pats.append(torch.randint(0, 3, (n, V), generator=g) - 1)
+    for p in pats:
+        env = torch.maximum(env, (O.blend(net, fv, rd, mk, e_ulp=p) - base).abs().max(dim=1)[0])
+    return base, env
