@@ -1,0 +1,63 @@
+"""world_size-2 gloo tests of the shard / all-gather logic (host side; no GPU)."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from surf_b200 import dist as sdist
+
+
+def test_shard_rays_covers_and_aligns():
+    for n in (1, 255, 256, 257, 28800, 460800, 460801):
+        for world in (1, 2, 3, 4, 8):
+            spans = [sdist.shard_rays(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            for (a, b), (c, d) in zip(spans[:-1], spans[1:]):
+                assert b == c and a <= b
+            for a, b in spans:
+                assert a % 256 == 0 or a == n
+    assert [sdist.shard_planes(512, r, 8) for r in range(8)][3] == (192, 256)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n_rays, res, out_q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(0)
+        full = {"color_fine": torch.rand(n_rays, 3, generator=g), "val_normal": torch.rand(n_rays, 3, generator=g),
+                "sdf_depth": torch.rand(n_rays, 1, generator=g), "render_depth": torch.rand(n_rays, generator=g)}
+        r0, r1 = sdist.shard_rays(n_rays, rank, world)
+        local = {k: v[r0:r1] for k, v in full.items()}
+        got = sdist.gather_image(local, n_rays)
+        ok = all(torch.equal(got[k].reshape(full[k].shape), full[k]) for k in full)
+        u = torch.rand(res, res, res, generator=g)
+        x0, x1 = sdist.shard_planes(res, rank, world)
+        ok = ok and torch.equal(sdist.gather_grid(u[x0:x1], res), u)
+        out_q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gather_image_and_grid_gloo_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, 1000, 9, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    results = dict(q.get(timeout=10) for _ in range(2))
+    assert results == {0: True, 1: True}
