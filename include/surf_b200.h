@@ -212,6 +212,12 @@ int64_t surf_launch_count(void);
 int surf_timing_enable(int32_t on);
 int surf_timing_read(double* ms_out /*[SURF_TIMING_KINDS]*/, int64_t* launches_out /*[SURF_TIMING_KINDS]*/);
 
+/* Diagnostic: one 128 x N x K GEMM through the tcgen05 building blocks of the tensor-core MLP kernels
+ * (A operand in TMEM, B in shared memory, fp32 accumulate in TMEM).  D (128,N) = A (128,K) * B (N,K)^T,
+ * all fp32 row-major device buffers; split != 0 uses the fp16 hi/lo 3-MMA scheme of the fp32-parity mode. */
+int surf_tc_selftest(const float* d_A, const float* d_B, float* d_D, int32_t K, int32_t N, int32_t split,
+                     void* stream);
+
 #ifdef __cplusplus
 }
 #endif

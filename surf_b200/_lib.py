@@ -25,6 +25,7 @@ EXPORTS = [
     "surf_render_workspace_bytes", "surf_sample_rays", "surf_render_core", "surf_render_rays",
     "surf_sdf_points", "surf_sdf_grid",
     "surf_point_mask", "surf_lookup_sparse", "surf_lookup_feature", "surf_blend", "surf_point_flags",
+    "surf_tc_selftest",
 ]
 
 
@@ -154,6 +155,8 @@ def _declare(lib):
     lib.surf_lookup_feature.argtypes = [vp, vp, i64, vp, vp, vp, vp]
     lib.surf_blend.restype = C.c_int
     lib.surf_blend.argtypes = [vp, vp, vp, vp, i64, i32, vp, vp]
+    lib.surf_tc_selftest.restype = C.c_int
+    lib.surf_tc_selftest.argtypes = [vp, vp, vp, i32, i32, i32, vp]
     lib.surf_point_flags.restype = C.c_int
     lib.surf_point_flags.argtypes = [vp, P(RenderCfg), vp, vp, vp, i64, i32, vp, vp, vp, C.c_size_t, vp]
 
