@@ -50,6 +50,8 @@ def parse():
     ap.add_argument("--cpu-rays", type=int, default=8192, help="rays per CPU-baseline sample / reference-arm step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--mlp-mode", type=int, default=1, choices=[0, 1],
+                    help="0 = fp32 FFMA SDF-MLP kernels, 1 = tcgen05 kernels where available")
     return ap.parse_args()
 
 
@@ -237,6 +239,7 @@ def run_gpu(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
+    _lib.set_mlp_mode(args.mlp_mode)
 
     # ---- scene + network (generated on the device; scene_prepare timed separately) ----------------
     # weak scaling: rank r renders the image of "scene r" (same shape, different seed)

@@ -212,6 +212,12 @@ int64_t surf_launch_count(void);
 int surf_timing_enable(int32_t on);
 int surf_timing_read(double* ms_out /*[SURF_TIMING_KINDS]*/, int64_t* launches_out /*[SURF_TIMING_KINDS]*/);
 
+/* Process-wide choice of the SDF-MLP kernel family: 0 = fp32 FFMA (default), 1 = tcgen05 tensor cores with the
+ * fp16 hi/lo 3-MMA split (fp32-grade accuracy, bitwise reproducible), 2 = same with two MMA-issuing threads per
+ * tile (faster; the fp32 accumulation order then depends on timing, results reproducible to ~1e-7 only).
+ * Kernels without a tensor-core edition keep using mode 0. */
+int surf_set_mlp_mode(int32_t mode);
+
 /* Diagnostic: one 128 x N x K GEMM through the tcgen05 building blocks of the tensor-core MLP kernels
  * (A operand in TMEM, B in shared memory, fp32 accumulate in TMEM).  D (128,N) = A (128,K) * B (N,K)^T,
  * all fp32 row-major device buffers; split != 0 uses the fp16 hi/lo 3-MMA scheme of the fp32-parity mode. */

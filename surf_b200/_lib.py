@@ -25,7 +25,7 @@ EXPORTS = [
     "surf_render_workspace_bytes", "surf_sample_rays", "surf_render_core", "surf_render_rays",
     "surf_sdf_points", "surf_sdf_grid",
     "surf_point_mask", "surf_lookup_sparse", "surf_lookup_feature", "surf_blend", "surf_point_flags",
-    "surf_tc_selftest",
+    "surf_tc_selftest", "surf_set_mlp_mode",
 ]
 
 
@@ -155,6 +155,8 @@ def _declare(lib):
     lib.surf_lookup_feature.argtypes = [vp, vp, i64, vp, vp, vp, vp]
     lib.surf_blend.restype = C.c_int
     lib.surf_blend.argtypes = [vp, vp, vp, vp, i64, i32, vp, vp]
+    lib.surf_set_mlp_mode.restype = C.c_int
+    lib.surf_set_mlp_mode.argtypes = [i32]
     lib.surf_tc_selftest.restype = C.c_int
     lib.surf_tc_selftest.argtypes = [vp, vp, vp, i32, i32, i32, vp]
     lib.surf_point_flags.restype = C.c_int
@@ -207,3 +209,8 @@ def timing_read():
     n = (C.c_int64 * len(TIMING_KINDS))()
     check(load().surf_timing_read(ms, n), "timing_read")
     return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(TIMING_KINDS)}
+
+
+def set_mlp_mode(mode: int):
+    """0 = fp32 FFMA kernels, 1 = tcgen05 tensor-core kernels (fp16 hi/lo split, fp32-grade accuracy)."""
+    check(load().surf_set_mlp_mode(int(mode)), "set_mlp_mode")

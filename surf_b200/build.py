@@ -16,7 +16,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB = os.path.join(CSRC, "libsurf_b200.so")
-SOURCES = ["scene.cu", "sample.cu", "sdf_mlp.cu", "blend.cu", "render.cu", "tc_selftest.cu"]
+SOURCES = ["scene.cu", "sample.cu", "sdf_mlp.cu", "blend.cu", "render.cu", "tc_selftest.cu", "sdf_tc.cu"]
+EXTRA = os.environ.get("SURF_NVCC_EXTRA", "").split()
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 
@@ -45,7 +46,7 @@ def build(force=False, verbose=False):
         o = os.path.join(CSRC, src.replace(".cu", ".o"))
         objs.append(o)
         if force or _stale(o, [s] + headers):
-            cmd = [nvcc, "-O3", "-std=c++17", "-lineinfo", *ARCH, "-Xcompiler", "-fPIC", "-I", INCLUDE, "-I", CSRC,
+            cmd = [nvcc, "-O3", "-std=c++17", "-lineinfo", *ARCH, *EXTRA, "-Xcompiler", "-fPIC", "-I", INCLUDE, "-I", CSRC,
                    "-c", s, "-o", o]
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")

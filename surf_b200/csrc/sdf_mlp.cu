@@ -436,6 +436,17 @@ static inline int perm_pos_128(int n) {   // column n -> position inside a permu
   return 64 * (jj >> 2) + tx * 4 + (jj & 3);
 }
 
+int surf_build_tc_weights(const std::vector<std::vector<float>>& W, const surf_net_inputs* in, surf_net* net,
+                          cudaStream_t st, int (*dev_alloc)(surf_net*, void**, size_t));
+
+static int g_mlp_mode = 0;
+int surf_mlp_mode() { return g_mlp_mode; }
+extern "C" int surf_set_mlp_mode(int32_t mode) {
+  SURF_CHECK_ARG(mode >= 0 && mode <= 2, "mlp mode must be 0 (fp32 FFMA), 1 (tcgen05) or 2 (tcgen05, two issuers)");
+  g_mlp_mode = mode;
+  return 0;
+}
+
 int surf_build_sdf_weights(const surf_net_inputs* in, surf_net* net, cudaStream_t st,
                            int (*dev_alloc)(surf_net*, void**, size_t)) {
   SURF_CHECK_ARG(in->n_lin == SURF_SDF_LAYERS, "n_lin must be 7");
@@ -544,6 +555,11 @@ int surf_build_sdf_weights(const surf_net_inputs* in, surf_net* net, cudaStream_
   SURF_CUDA(cudaMemcpyAsync(p, w6.data(), w6.size() * sizeof(float), cudaMemcpyHostToDevice, st));
   net->dev.w6 = (const float*)p;
   SURF_CUDA(cudaStreamSynchronize(st));   // host vectors go out of scope
+  net->tc_ok = (in->multires == 4 && skip == 3) ? 1 : 0;
+  if (net->tc_ok) {
+    rc = surf_build_tc_weights(W, in, net, st, dev_alloc);
+    if (rc) return rc;
+  }
   net->dev.b6 = in->h_bias[6][0];
   net->dev.scale = in->scale;
   net->dev.inv_scale = 1.0f / in->scale;
@@ -565,6 +581,7 @@ int launch_sdf_mlp(const surf_scene* s, const surf_net* n, const PointSource& sr
     attr_set = true;
   }
   if (src.n <= 0) return 0;
+  if (!d_grad && g_mlp_mode >= 1 && n->tc_ok) return launch_sdf_tc_fwd(s, n, src, d_sdf, negate, st);
   int64_t tiles = (src.n + MLP_TILE - 1) / MLP_TILE;
   int grid = (int)(tiles < n->n_sm ? tiles : n->n_sm);
   surf_time_begin(d_grad ? 0 : 1, st);

@@ -78,6 +78,8 @@ struct surf_net {
   DevNet dev;
   void* owned[16];
   int n_owned;
+  const uint8_t* tc_blob;           // tensor-core weight stream (fp16 hi/lo chunks, sdf_tc.cu)
+  int tc_ok;                        // network shape supported by the tensor-core kernels
   float* scratch;                   // sigma' scratch for the backward pass (per-CTA private)
   size_t scratch_bytes;
   int n_sm;
@@ -246,6 +248,9 @@ struct PointSource {
 
 int launch_sdf_mlp(const surf_scene* s, const surf_net* n, const PointSource& src, float* d_sdf, float* d_grad,
                    bool negate, cudaStream_t st);
+int launch_sdf_tc_fwd(const surf_scene* s, const surf_net* n, const PointSource& src, float* d_sdf, bool negate,
+                      cudaStream_t st);
+int surf_mlp_mode();   // 0 = fp32 FFMA kernels, 1 = tcgen05 kernels (fp16 hi/lo split, fp32-grade)
 int launch_lookup_feature(const surf_scene* s, const PointSource& src, float* d_feat, float* d_raydiff,
                           uint8_t* d_mask, bool packed19, cudaStream_t st);
 int launch_blend(const surf_scene* s_or_null, const surf_net* n, const float* d_feat, const float* d_raydiff,

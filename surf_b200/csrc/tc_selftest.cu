@@ -86,3 +86,64 @@ extern "C" int surf_tc_selftest(const float* d_A, const float* d_B, float* d_D, 
   SURF_LAUNCH_CHECK();
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------
+// micro-benchmark: cycles for `reps` back-to-back tcgen05.mma (M=128, N, K=16), one CTA.
+//   mode 0: TS, one accumulator (dependent chain)      mode 1: TS, two alternating accumulators
+//   mode 2: SS, one accumulator                        mode 3: SS, two alternating accumulators
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1) k_tc_bench(int N, int reps, int mode, long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint32_t s_tmem;
+  __shared__ __align__(8) uint64_t s_bar;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (warp == 0) tc::tmem_alloc<512>(&s_tmem);
+  if (tid == 0) {
+    tc::mbar_init(&s_bar, mode >= 4 ? mode - 3 : 1);
+    tc::mbar_fence_init();
+  }
+  for (int i = tid; i < 16384; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  tc::fence_proxy_async();
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tbase = s_tmem;
+  // mode >= 4: (mode - 3) issuer threads (lane 0 of warps 0..), each with its own accumulator (N <= 128), TS form
+  const int n_issuers = mode >= 4 ? mode - 3 : 1;
+  if ((tid & 31) == 0 && warp < n_issuers) {
+    const uint32_t idesc = tc::idesc_f16(128, N, 0);
+    const uint64_t d0 = tc::smem_desc_kmajor(tc::smem_u32(smem), (uint32_t)N * 16, 128);
+    const uint32_t dlo = (uint32_t)d0, dhi = (uint32_t)(d0 >> 32);
+    const uint64_t a0 = tc::smem_desc_kmajor(tc::smem_u32(smem) + 32768, 2048, 128);
+    const uint32_t alo = (uint32_t)a0, ahi = (uint32_t)(a0 >> 32);
+    const long long t0 = clock64();
+    for (int r = 0; r < reps; ++r) {
+      uint32_t tD = tbase + (((mode & 1) && mode < 4 && (r & 1)) ? 256 : 0);
+      if (mode >= 4) tD = tbase + warp * 128;
+      if (mode < 2 || mode >= 4) tc::mma_ts_w<true>(tD, tbase + 448, dlo, dhi, idesc);
+      else tc::mma_ss_w<true>(tD, alo, ahi, dlo, dhi, idesc);
+    }
+    const long long t1 = clock64();
+    tc::mma_commit(&s_bar);
+    tc::mbar_wait(&s_bar, 0);
+    const long long t2 = clock64();
+    if (warp == 0) {
+      out[0] = t1 - t0;
+      out[1] = t2 - t0;
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc<512>(tbase);
+}
+
+extern "C" int surf_tc_bench(int32_t N, int32_t reps, int32_t mode, long long* h_out) {
+  long long* d = nullptr;
+  SURF_CUDA(cudaMalloc((void**)&d, 16));
+  SURF_CUDA(cudaFuncSetAttribute(k_tc_bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+  for (int it = 0; it < 2; ++it) k_tc_bench<<<1, 128, 65536>>>(N, reps, mode, d);
+  SURF_CUDA(cudaDeviceSynchronize());
+  SURF_CUDA(cudaMemcpy(h_out, d, 16, cudaMemcpyDeviceToHost));
+  cudaFree(d);
+  return 0;
+}
