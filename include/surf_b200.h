@@ -214,7 +214,8 @@ int surf_timing_read(double* ms_out /*[SURF_TIMING_KINDS]*/, int64_t* launches_o
 
 /* Process-wide choice of the SDF-MLP kernel family: 0 = fp32 FFMA (default), 1 = tcgen05 tensor cores with the
  * fp16 hi/lo 3-MMA split (fp32-grade accuracy, bitwise reproducible), 2 = same with two MMA-issuing threads per
- * tile (faster; the fp32 accumulation order then depends on timing, results reproducible to ~1e-7 only).
+ * tile (experimental; the fp32 accumulation order then depends on timing), 3 = tcgen05 with the one-tile kernel
+ * (sdf_tc1.cu) for the forward-only queries too (the gradient path always uses it in modes >= 1).
  * Kernels without a tensor-core edition keep using mode 0. */
 int surf_set_mlp_mode(int32_t mode);
 

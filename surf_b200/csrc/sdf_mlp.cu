@@ -439,10 +439,13 @@ static inline int perm_pos_128(int n) {   // column n -> position inside a permu
 int surf_build_tc_weights(const std::vector<std::vector<float>>& W, const surf_net_inputs* in, surf_net* net,
                           cudaStream_t st, int (*dev_alloc)(surf_net*, void**, size_t));
 
+int surf_build_tc1_weights(const std::vector<std::vector<float>>& W, const surf_net_inputs* in, surf_net* net,
+                           cudaStream_t st, int (*dev_alloc)(surf_net*, void**, size_t));
+
 static int g_mlp_mode = 0;
 int surf_mlp_mode() { return g_mlp_mode; }
 extern "C" int surf_set_mlp_mode(int32_t mode) {
-  SURF_CHECK_ARG(mode >= 0 && mode <= 2, "mlp mode must be 0 (fp32 FFMA), 1 (tcgen05) or 2 (tcgen05, two issuers)");
+  SURF_CHECK_ARG(mode >= 0 && mode <= 3, "mlp mode must be 0..3");
   g_mlp_mode = mode;
   return 0;
 }
@@ -559,6 +562,8 @@ int surf_build_sdf_weights(const surf_net_inputs* in, surf_net* net, cudaStream_
   if (net->tc_ok) {
     rc = surf_build_tc_weights(W, in, net, st, dev_alloc);
     if (rc) return rc;
+    rc = surf_build_tc1_weights(W, in, net, st, dev_alloc);
+    if (rc) return rc;
   }
   net->dev.b6 = in->h_bias[6][0];
   net->dev.scale = in->scale;
@@ -581,7 +586,10 @@ int launch_sdf_mlp(const surf_scene* s, const surf_net* n, const PointSource& sr
     attr_set = true;
   }
   if (src.n <= 0) return 0;
-  if (!d_grad && g_mlp_mode >= 1 && n->tc_ok) return launch_sdf_tc_fwd(s, n, src, d_sdf, negate, st);
+  if (g_mlp_mode >= 1 && n->tc_ok) {
+    if (d_grad || g_mlp_mode == 3) return launch_sdf_tc1(s, n, src, d_sdf, d_grad, negate, st);
+    return launch_sdf_tc_fwd(s, n, src, d_sdf, negate, st);
+  }
   int64_t tiles = (src.n + MLP_TILE - 1) / MLP_TILE;
   int grid = (int)(tiles < n->n_sm ? tiles : n->n_sm);
   surf_time_begin(d_grad ? 0 : 1, st);

@@ -1,0 +1,613 @@
+// K2a + K3, tensor-core edition, one 128-point tile per CTA pass: forward + analytic input gradient.
+//   reference: SDFNetworkSparse.sdf / .gradient (sdf_network.py:95-141), lookup_sparse_volume (projector.py:217-390)
+//
+// TMEM map (512 columns): two fp32 accumulators D_a [0,160) and D_b [160,320) — one per MMA-issuing thread, so the
+// two threads needed to keep the tensor pipe fed (tools/tc_bench.py: one thread sustains one MMA per ~100-120 clk,
+// the pipe takes ~69 clk for M128 N128 K16) never accumulate into the same tile and the result stays bitwise
+// deterministic (the epilogue adds D_a + D_b) — and the fp16 hi / lo halves of the A operand [320,384) / [384,448).
+// 16 epilogue warps: warp (q, part) owns TMEM lane quarter q (32 points) and 32 of the 128 columns.
+// Forward: as sdf_tc.cu.  Reverse pass: delta_l (128 x 128) is the A operand, the transposed weights stream as
+// N = 160 (128 hidden + 28 feature-gradient + 4 pad) x K = 32 chunks, softplus' is parked as unorm16 in a per-CTA
+// L2-resident scratch, the feature-gradient columns are accumulated in registers across layers.
+#include <math.h>
+#include <string.h>
+
+#include <vector>
+
+#include "surf_internal.cuh"
+#include "tc_common.cuh"
+
+#define T1_EPI_WARPS 16
+#define T1_EPI_THREADS (T1_EPI_WARPS * 32)
+#define T1_THREADS ((T1_EPI_WARPS + 3) * 32)     // + 2 MMA issuers + 1 weight loader
+#define T1_SLOT_BYTES 20480                      // N = 160 x K = 32 x (hi + lo)
+#define T1_NSLOT 7
+#define T1_MAXCHUNK 64
+
+#define T1_DA 0u
+#define T1_DB 160u
+#define T1_AHI 320u
+#define T1_ALO 384u
+
+// dynamic smem (bytes)
+#define S1_RING 0
+#define S1_AFEAT (S1_RING + T1_NSLOT * T1_SLOT_BYTES)      // hi 8 KB | lo 8 KB  (128 rows x K 32)
+#define S1_APE (S1_AFEAT + 16384)
+#define S1_W6 (S1_APE + 16384)                             // 160 floats
+#define S1_PART (S1_W6 + 640)                              // [4][128] floats
+#define S1_GPE (S1_PART + 2048)                            // [28][128] floats
+#define S1_GF (S1_GPE + 14336)                             // [28][128] floats ; later [4][3][128] partial grads
+#define S1_BAR (S1_GF + 14336)
+#define S1_TOTAL (S1_BAR + 256)
+
+struct T1Stream {
+  int n_fwd, n_all;
+  uint32_t off[T1_MAXCHUNK];      // byte offset in the blob
+  uint32_t bytes[T1_MAXCHUNK];
+};
+
+struct T1Bars {
+  uint64_t w_full[T1_NSLOT];
+  uint64_t w_empty[T1_NSLOT];
+  uint64_t d_full;
+  uint64_t a_ready;
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ float t1_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float t1_lg2(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float t1_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// softplus(beta=100) and its derivative sigmoid(100 z), branch-free (see sdf_tc.cu)
+template <bool GRAD>
+__device__ __forceinline__ float t1_softplus(float z, float& dh) {
+  const float e = t1_ex2(fabsf(z) * -144.26950408889634f);
+  const float u = 1.0f + e;
+  if (GRAD) {
+    const float r = t1_rcp(u);
+    dh = (z >= 0.f) ? r : 1.0f - r;
+  }
+  return fmaf(t1_lg2(u), 0.0069314718055994531f, fmaxf(z, 0.f));
+}
+
+// chunk layout per layer phase of the weight stream
+__device__ __forceinline__ int t1_phase_chunks(int phase) {   // phases 0..5 fwd, 6..10 reverse lin5..lin1, 11 reverse lin0
+  if (phase == 0) return 1;
+  if (phase < 6) return 5;
+  if (phase < 11) return 4;
+  return 2;
+}
+
+template <bool GRAD>
+__global__ void __launch_bounds__(T1_THREADS, 1)
+k_sdf_tc1(const DevScene sc, const DevNet net, const PointSource src, const uint8_t* __restrict__ wblob,
+          const T1Stream stream, float* __restrict__ sdf_out, float* __restrict__ grad_out,
+          uint4* __restrict__ scratch_all, int negate) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  T1Bars* bars = reinterpret_cast<T1Bars*>(smem + S1_BAR);
+  float* sw6 = reinterpret_cast<float*>(smem + S1_W6);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int NPHASE = GRAD ? 12 : 6;
+  const int nch_tile = GRAD ? stream.n_all : stream.n_fwd;
+
+  int64_t n_total = src.n;
+  if (src.count) {
+    const int64_t c = *src.count;
+    n_total = c < n_total ? c : n_total;
+  }
+  const int64_t n_tiles = (n_total + 127) / 128;
+  int64_t my_tiles = 0;
+  if ((int64_t)blockIdx.x < n_tiles) my_tiles = (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+
+  if (warp == T1_EPI_WARPS) tc::tmem_alloc<512>(&bars->tmem_base);
+  if (tid == 0) {
+    for (int i = 0; i < T1_NSLOT; ++i) {
+      tc::mbar_init(&bars->w_full[i], 1);
+      tc::mbar_init(&bars->w_empty[i], 1);
+    }
+    tc::mbar_init(&bars->d_full, 2);
+    tc::mbar_init(&bars->a_ready, T1_EPI_THREADS);
+    tc::mbar_fence_init();
+  }
+  for (int i = tid; i < 160; i += T1_THREADS) sw6[i] = net.w6[i];
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tbase = bars->tmem_base;
+
+  if (warp < T1_EPI_WARPS) {
+    // =============================== epilogue / staging warps ===============================
+    const int q = warp & 3, part = warp >> 2;
+    const int r = q * 32 + lane;                 // row = point = TMEM lane
+    const int c0 = part * 32;                    // first of my 32 hidden columns
+    const uint32_t tl = tbase + ((uint32_t)(q * 32) << 16);
+    uint8_t* afeat = smem + S1_AFEAT;
+    uint8_t* ape = smem + S1_APE;
+    float* s_part = reinterpret_cast<float*>(smem + S1_PART);
+    float* s_gpe = reinterpret_cast<float*>(smem + S1_GPE);
+    float* s_gf = reinterpret_cast<float*>(smem + S1_GF);
+    uint4* scratch = scratch_all + (size_t)blockIdx.x * (5 * 4 * T1_EPI_THREADS);
+    const int te = warp * 32 + lane;             // 0..511
+    uint32_t ph_d = 0;
+    auto put_k = [&](uint8_t* base, int k, float v) {
+      const __half h = __float2half_rn(v);
+      const __half l = __float2half_rn(v - __half2float(h));
+      const uint32_t off = (uint32_t)(k >> 3) * 2048u + r * 16 + (k & 7) * 2;
+      *reinterpret_cast<__half*>(base + off) = h;
+      *reinterpret_cast<__half*>(base + 8192 + off) = l;
+    };
+    auto get_k = [&](const uint8_t* base, int k) {
+      const uint32_t off = (uint32_t)(k >> 3) * 2048u + r * 16 + (k & 7) * 2;
+      return __half2float(*reinterpret_cast<const __half*>(base + off)) +
+             __half2float(*reinterpret_cast<const __half*>(base + 8192 + off));
+    };
+    auto epi_bar = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(T1_EPI_THREADS) : "memory"); };
+
+    for (int64_t it = 0; it < my_tiles; ++it) {
+      const int64_t tile = (int64_t)blockIdx.x + it * gridDim.x;
+      const int64_t i = tile * 128 + r;
+      float px = 0.f, py = 0.f, pz = 0.f;
+      int64_t id = -1;
+      if (i < n_total) {
+        id = src.list ? (int64_t)src.list[i] : i;
+        if (src.mode == 0) {
+          px = src.pts[id * 3]; py = src.pts[id * 3 + 1]; pz = src.pts[id * 3 + 2];
+        } else if (src.mode == 1) {
+          const int64_t ray = id / src.S;
+          const float t = src.mid_z[id];
+          px = ray_at(src.rays_o[ray * 3], src.rays_d[ray * 3], t);
+          py = ray_at(src.rays_o[ray * 3 + 1], src.rays_d[ray * 3 + 1], t);
+          pz = ray_at(src.rays_o[ray * 3 + 2], src.rays_d[ray * 3 + 2], t);
+        } else {
+          const int64_t yz = (int64_t)src.ny * src.nz;
+          const int xi = (int)(id / yz);
+          const int rem = (int)(id - (int64_t)xi * yz);
+          px = src.xs[xi]; py = src.ys[rem / src.nz]; pz = src.zs[rem % src.nz];
+        }
+      }
+      // ---- staging: thread (row, part) gathers level `part` and encodes PE frequency `part` ----
+      {
+        float f7[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (part < sc.n_levels) sparse_level<0>(sc, part, px, py, pz, nullptr, f7);
+#pragma unroll
+        for (int c = 0; c < 7; ++c) put_k(afeat, part * 7 + c, f7[c]);
+        const float xs[3] = {px * net.scale, py * net.scale, pz * net.scale};
+        if (part == 0) {
+#pragma unroll
+          for (int d = 0; d < 3; ++d) put_k(ape, d, xs[d]);
+        }
+        if (part == 3) {
+          put_k(afeat, 28, 1.0f);
+          put_k(ape, 27, 1.0f);
+#pragma unroll
+          for (int k = 29; k < 32; ++k) put_k(afeat, k, 0.f);
+#pragma unroll
+          for (int k = 28; k < 32; ++k) put_k(ape, k, 0.f);
+        }
+        const float fr = (float)(1 << part);
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          float sn = 0.f, cs = 0.f;
+          if (part < net.multires) sincosf(xs[d] * fr, &sn, &cs);
+          put_k(ape, 3 + 6 * part + d, sn);
+          put_k(ape, 3 + 6 * part + 3 + d, cs);
+        }
+      }
+      tc::fence_proxy_async();
+      tc::tc_fence_before();
+      tc::mbar_arrive(&bars->a_ready);
+
+      float gf[8];          // reverse pass: d sdf / d feat for feature columns part*8 .. part*8+7
+      // ------------------------------------ forward ------------------------------------
+      for (int l = 0; l < 6; ++l) {
+        tc::mbar_wait(&bars->d_full, ph_d & 1);
+        ph_d++;
+        tc::tc_fence_after();
+        const bool to_skip = (l + 1 == net.skip_layer);
+        float head = 0.f;
+        uint32_t sp[16];      // softplus' of my 32 columns as unorm16 pairs
+#pragma unroll
+        for (int hb = 0; hb < 2; ++hb) {           // two 16-column blocks
+          const int cb = c0 + hb * 16;
+          uint32_t a[16], b[16];
+          tc::tmem_ld16(tl + T1_DA + cb, a);
+          if (l > 0) tc::tmem_ld16(tl + T1_DB + cb, b);
+          tc::tmem_wait_ld();
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float z0 = __uint_as_float(a[2 * j]), z1 = __uint_as_float(a[2 * j + 1]);
+            if (l > 0) {
+              z0 += __uint_as_float(b[2 * j]);
+              z1 += __uint_as_float(b[2 * j + 1]);
+            }
+            float d0 = 0.f, d1 = 0.f;
+            float h0 = t1_softplus<GRAD>(z0, d0);
+            float h1 = t1_softplus<GRAD>(z1, d1);
+            const int n0 = cb + 2 * j;
+            if (to_skip && part == 3) {            // columns 101..127 of the skip layer's input are the PE
+              if (n0 >= 101) { h0 = get_k(ape, n0 - 101); d0 = 0.f; }
+              if (n0 + 1 >= 101) { h1 = get_k(ape, n0 + 1 - 101); d1 = 0.f; }
+            }
+            if (l == 5) {
+              head = fmaf(h0, sw6[n0], head);
+              head = fmaf(h1, sw6[n0 + 1], head);
+              if (GRAD) {                          // delta5 = w6[n] / scale * softplus'(z5)
+                h0 = sw6[n0] * net.inv_scale * d0;
+                h1 = sw6[n0 + 1] * net.inv_scale * d1;
+              }
+            } else if (GRAD) {
+              const uint32_t u0 = __float2uint_rn(d0 * 65535.0f), u1 = __float2uint_rn(d1 * 65535.0f);
+              sp[hb * 8 + j] = u0 | (u1 << 16);
+            }
+            tc::split2(h0, h1, hi[j], lo[j]);
+          }
+          if (l < 5 || GRAD) {
+            tc::tmem_st8(tl + T1_AHI + (cb >> 1), hi);
+            tc::tmem_st8(tl + T1_ALO + (cb >> 1), lo);
+          }
+        }
+        if (l < 5 || GRAD) {
+          tc::tmem_wait_st();
+          tc::tc_fence_before();
+          tc::mbar_arrive(&bars->a_ready);
+        }
+        if (GRAD && l < 5) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            scratch[(size_t)(l * 4 + j) * T1_EPI_THREADS + te] = make_uint4(sp[4 * j], sp[4 * j + 1], sp[4 * j + 2], sp[4 * j + 3]);
+        }
+        if (l == 5) {
+          s_part[part * 128 + r] = head;
+          epi_bar();
+          if (part == 0) {
+            float s = s_part[r] + s_part[128 + r] + s_part[256 + r] + s_part[384 + r] + net.b6;
+#pragma unroll
+            for (int c = 0; c < 28; ++c) s = fmaf(get_k(afeat, c), sw6[128 + c], s);
+            s *= net.inv_scale;
+            if (id >= 0) sdf_out[id] = negate ? -s : s;
+          }
+          if (!GRAD) {
+            tc::tc_fence_before();
+            epi_bar();            // afeat / s_part reads done before the next tile restages
+          }
+        }
+      }
+      if (!GRAD) continue;
+
+      // ------------------------------------ reverse ------------------------------------
+#pragma unroll
+      for (int j = 0; j < 8; ++j) gf[j] = sw6[128 + part * 8 + j] * net.inv_scale;
+      for (int l = 5; l >= 1; --l) {
+        // softplus'(z_{l-1}) of my columns (thread-private, written in the forward pass)
+        uint4 spv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) spv[j] = scratch[(size_t)((l - 1) * 4 + j) * T1_EPI_THREADS + te];
+        tc::mbar_wait(&bars->d_full, ph_d & 1);
+        ph_d++;
+        tc::tc_fence_after();
+        const uint32_t* spw = reinterpret_cast<const uint32_t*>(spv);
+        const bool is_skip = (l == net.skip_layer);
+#pragma unroll
+        for (int hb = 0; hb < 2; ++hb) {
+          const int cb = c0 + hb * 16;
+          uint32_t a[16], b[16];
+          tc::tmem_ld16(tl + T1_DA + cb, a);
+          tc::tmem_ld16(tl + T1_DB + cb, b);
+          tc::tmem_wait_ld();
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float g0 = __uint_as_float(a[2 * j]) + __uint_as_float(b[2 * j]);
+            const float g1 = __uint_as_float(a[2 * j + 1]) + __uint_as_float(b[2 * j + 1]);
+            const uint32_t w = spw[hb * 8 + j];
+            const float d0 = (float)(w & 0xffffu) * (1.0f / 65535.0f), d1 = (float)(w >> 16) * (1.0f / 65535.0f);
+            const int n0 = cb + 2 * j;
+            if (is_skip && part == 3) {            // input-gradient of the PE columns of the skip layer
+              if (n0 >= 101) s_gpe[(n0 - 101) * 128 + r] = g0;
+              if (n0 + 1 >= 101) s_gpe[(n0 + 1 - 101) * 128 + r] = g1;
+            }
+            tc::split2(g0 * d0, g1 * d1, hi[j], lo[j]);
+          }
+          tc::tmem_st8(tl + T1_AHI + (cb >> 1), hi);
+          tc::tmem_st8(tl + T1_ALO + (cb >> 1), lo);
+        }
+        {   // feature-gradient columns 128 + part*8 ..
+          uint32_t a[8], b[8];
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                       : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7])
+                       : "r"(tl + T1_DA + 128 + part * 8));
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                       : "=r"(b[0]), "=r"(b[1]), "=r"(b[2]), "=r"(b[3]), "=r"(b[4]), "=r"(b[5]), "=r"(b[6]), "=r"(b[7])
+                       : "r"(tl + T1_DB + 128 + part * 8));
+          tc::tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) gf[j] += __uint_as_float(a[j]) + __uint_as_float(b[j]);
+        }
+        tc::tmem_wait_st();
+        tc::tc_fence_before();
+        tc::mbar_arrive(&bars->a_ready);
+      }
+      // feature gradients -> smem (28 x 128)
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (part * 8 + j < 28) s_gf[(part * 8 + j) * 128 + r] = gf[j];
+      // ---- reverse of lin0: g_pe += delta0 . W0 (N = 32) ----
+      tc::mbar_wait(&bars->d_full, ph_d & 1);
+      ph_d++;
+      tc::tc_fence_after();
+      epi_bar();                                   // s_gpe (skip part) and s_gf complete
+      if (part == 0) {
+        uint32_t a[16], b[16];
+#pragma unroll
+        for (int hb = 0; hb < 2; ++hb) {
+          tc::tmem_ld16(tl + T1_DA + hb * 16, a);
+          tc::tmem_ld16(tl + T1_DB + hb * 16, b);
+          tc::tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int k = hb * 16 + j;
+            if (k < 27) s_gpe[k * 128 + r] += __uint_as_float(a[j]) + __uint_as_float(b[j]);
+          }
+        }
+      }
+      tc::tc_fence_before();
+      // d feats / d x for level `part` (re-gather; the data was touched ~50 us ago, L2 hits)
+      float o3[3] = {0.f, 0.f, 0.f};
+      if (part < sc.n_levels) {
+        float g7[7];
+#pragma unroll
+        for (int c = 0; c < 7; ++c) g7[c] = s_gf[(part * 7 + c) * 128 + r];
+        sparse_level<1>(sc, part, px, py, pz, g7, o3);
+      }
+      epi_bar();                                   // all s_gf reads done, s_gpe final
+      float* s_pg = s_gf;                          // reuse as [4][3][128]
+      s_pg[(part * 3 + 0) * 128 + r] = o3[0];
+      s_pg[(part * 3 + 1) * 128 + r] = o3[1];
+      s_pg[(part * 3 + 2) * 128 + r] = o3[2];
+      epi_bar();
+      if (part < 3 && id >= 0) {                   // thread (row, d = part) finishes component d
+        const int d = part;
+        float gx = s_gpe[d * 128 + r];
+        float fr = 1.0f;
+        for (int f = 0; f < net.multires; ++f) {
+          const float sn = get_k(ape, 3 + 6 * f + d), cs = get_k(ape, 3 + 6 * f + 3 + d);
+          gx += fr * (s_gpe[(3 + 6 * f + d) * 128 + r] * cs - s_gpe[(3 + 6 * f + 3 + d) * 128 + r] * sn);
+          fr *= 2.0f;
+        }
+        gx *= net.scale;
+#pragma unroll
+        for (int lv = 0; lv < 4; ++lv) gx += s_pg[(lv * 3 + d) * 128 + r];
+        grad_out[id * 3 + d] = gx;
+      }
+      epi_bar();                                   // smem scratch free for the next tile
+    }
+  } else if (warp < T1_EPI_WARPS + 2) {
+    // =============================== MMA issuers: sub 0 -> D_a, sub 1 -> D_b ===============================
+    const int sub = warp - T1_EPI_WARPS;
+    if (lane == 0) {
+      const uint32_t ring = tc::smem_u32(smem + S1_RING);
+      const uint32_t tD = tbase + (sub ? T1_DB : T1_DA);
+      const uint32_t tAhi = tbase + T1_AHI, tAlo = tbase + T1_ALO;
+      const uint32_t id128 = tc::idesc_f16(128, 128, 0), id160 = tc::idesc_f16(128, 160, 0), id32 = tc::idesc_f16(128, 32, 0);
+      // descriptor constant parts: SBO 128; LBO = rows * 16
+      const uint64_t d128 = tc::smem_desc_kmajor(0, 2048, 128), d160 = tc::smem_desc_kmajor(0, 2560, 128),
+                     d32 = tc::smem_desc_kmajor(0, 512, 128);
+      const uint32_t afeat_lo = (uint32_t)d128 | (tc::smem_u32(smem + S1_AFEAT) >> 4);
+      const uint32_t ape_lo = (uint32_t)d128 | (tc::smem_u32(smem + S1_APE) >> 4);
+      uint32_t ph_a = 0;
+      int64_t s = 0;
+      for (int64_t it = 0; it < my_tiles; ++it) {
+        for (int p = 0; p < NPHASE; ++p) {
+          const int nch = t1_phase_chunks(p);
+          tc::mbar_wait(&bars->a_ready, ph_a & 1);
+          ph_a++;
+          tc::tc_fence_after();
+          for (int c = 0; c < nch; ++c, ++s) {
+            if ((c & 1) != sub) continue;
+            const int slot = (int)(s % T1_NSLOT);
+            tc::mbar_wait(&bars->w_full[slot], (uint32_t)((s / T1_NSLOT) & 1));
+            const uint32_t wa = (ring + slot * T1_SLOT_BYTES) >> 4;       // 16-byte units
+            const bool first = (c == sub);                                  // first chunk of this accumulator
+            if (p < 6) {
+              // forward chunk: N = 128, K = 32 ; hi at +0, lo at +8192 B ; K step = 2 groups = 4096 B
+              const uint32_t w0 = (uint32_t)d128 | wa, dh = (uint32_t)(d128 >> 32);
+              if (p == 0 || c == 4) {
+                const uint32_t a0 = (p == 0) ? ape_lo : afeat_lo;
+                if (first) tc::mma_ss_w<false>(tD, a0, dh, w0, dh, id128); else tc::mma_ss_w<true>(tD, a0, dh, w0, dh, id128);
+                tc::mma_ss_w<true>(tD, a0 + 512, dh, w0, dh, id128);
+                tc::mma_ss_w<true>(tD, a0, dh, w0 + 512, dh, id128);
+                tc::mma_ss_w<true>(tD, a0 + 256, dh, w0 + 256, dh, id128);
+                tc::mma_ss_w<true>(tD, a0 + 768, dh, w0 + 256, dh, id128);
+                tc::mma_ss_w<true>(tD, a0 + 256, dh, w0 + 768, dh, id128);
+              } else {
+                const uint32_t ah = tAhi + c * 16, al = tAlo + c * 16;
+                if (first) tc::mma_ts_w<false>(tD, ah, w0, dh, id128); else tc::mma_ts_w<true>(tD, ah, w0, dh, id128);
+                tc::mma_ts_w<true>(tD, al, w0, dh, id128);
+                tc::mma_ts_w<true>(tD, ah, w0 + 512, dh, id128);
+                tc::mma_ts_w<true>(tD, ah + 8, w0 + 256, dh, id128);
+                tc::mma_ts_w<true>(tD, al + 8, w0 + 256, dh, id128);
+                tc::mma_ts_w<true>(tD, ah + 8, w0 + 768, dh, id128);
+              }
+            } else if (p < 11) {
+              // reverse chunk: N = 160, K = 32 ; hi at +0, lo at +10240 B ; K step = 2 groups = 5120 B
+              const uint32_t w0 = (uint32_t)d160 | wa, dh = (uint32_t)(d160 >> 32);
+              const uint32_t ah = tAhi + c * 16, al = tAlo + c * 16;
+              if (first) tc::mma_ts_w<false>(tD, ah, w0, dh, id160); else tc::mma_ts_w<true>(tD, ah, w0, dh, id160);
+              tc::mma_ts_w<true>(tD, al, w0, dh, id160);
+              tc::mma_ts_w<true>(tD, ah, w0 + 640, dh, id160);
+              tc::mma_ts_w<true>(tD, ah + 8, w0 + 320, dh, id160);
+              tc::mma_ts_w<true>(tD, al + 8, w0 + 320, dh, id160);
+              tc::mma_ts_w<true>(tD, ah + 8, w0 + 960, dh, id160);
+            } else {
+              // reverse of lin0: N = 32, K = 64 per chunk (4 K steps) ; hi at +0, lo at +4096 B ; K step = 1024 B
+              const uint32_t w0 = (uint32_t)d32 | wa, dh = (uint32_t)(d32 >> 32);
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                const uint32_t ah = tAhi + c * 32 + ks * 8, al = tAlo + c * 32 + ks * 8;
+                if (first && ks == 0) tc::mma_ts_w<false>(tD, ah, w0, dh, id32); else tc::mma_ts_w<true>(tD, ah, w0 + ks * 64, dh, id32);
+                tc::mma_ts_w<true>(tD, al, w0 + ks * 64, dh, id32);
+                tc::mma_ts_w<true>(tD, ah, w0 + 256 + ks * 64, dh, id32);
+              }
+            }
+            tc::mma_commit(&bars->w_empty[slot]);
+          }
+          tc::mma_commit(&bars->d_full);
+        }
+      }
+    }
+  } else {
+    // =============================== weight loader ===============================
+    if (lane == 0) {
+      const int64_t total = my_tiles * nch_tile;
+      for (int64_t s = 0; s < total; ++s) {
+        const int slot = (int)(s % T1_NSLOT);
+        const int cid = (int)(s % nch_tile);
+        if (s >= T1_NSLOT) tc::mbar_wait(&bars->w_empty[slot], (uint32_t)(((s / T1_NSLOT) - 1) & 1));
+        tc::mbar_arrive_expect_tx(&bars->w_full[slot], stream.bytes[cid]);
+        tc::bulk_g2s(smem + S1_RING + slot * T1_SLOT_BYTES, wblob + stream.off[cid], stream.bytes[cid],
+                     &bars->w_full[slot]);
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == T1_EPI_WARPS) tc::tmem_dealloc<512>(tbase);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host: combined forward + reverse weight stream
+// ---------------------------------------------------------------------------------------------
+static inline uint16_t t1_f2h(float f) {
+  __half h = __float2half_rn(f);
+  uint16_t b;
+  memcpy(&b, &h, 2);
+  return b;
+}
+static inline float t1_h2f(uint16_t b) {
+  __half h;
+  memcpy(&h, &b, 2);
+  return __half2float(h);
+}
+
+static T1Stream g_t1_stream;     // identical for every net of the supported shape; filled at build time
+
+int surf_build_tc1_weights(const std::vector<std::vector<float>>& W, const surf_net_inputs* in, surf_net* net,
+                           cudaStream_t st, int (*dev_alloc)(surf_net*, void**, size_t)) {
+  T1Stream& S = g_t1_stream;
+  memset(&S, 0, sizeof(S));
+  std::vector<uint16_t> blob;
+  int nc = 0;
+  // element (n, kk) of a chunk with `rows` N-rows: hi half at [0, half_bytes), lo half after it
+  auto add_chunk = [&](int rows, int K) {
+    const size_t half = (size_t)rows * K;           // halves
+    S.off[nc] = (uint32_t)(blob.size() * 2);
+    S.bytes[nc] = (uint32_t)(half * 2 * 2);
+    blob.resize(blob.size() + half * 2, 0);
+    return blob.size() - half * 2;
+  };
+  auto put = [&](size_t base, int rows, int K, int n, int kk, float v) {
+    const uint16_t hi = t1_f2h(v);
+    const uint16_t lo = t1_f2h(v - t1_h2f(hi));
+    const size_t off = (size_t)(kk >> 3) * rows * 8 + (size_t)n * 8 + (kk & 7);
+    blob[base + off] = hi;
+    blob[base + (size_t)rows * K + off] = lo;
+  };
+  // forward: lin0 (K = 27 + bias), lin1..lin5 (5 chunks of K = 32: 128 hidden | 28 feats + bias + pad)
+  {
+    const int O = in->out_dim[0], I = in->in_dim[0];
+    const size_t b = add_chunk(128, 32);
+    for (int n = 0; n < O && n < 128; ++n) {
+      for (int k = 0; k < I; ++k) put(b, 128, 32, n, k, W[0][(size_t)n * I + k]);
+      put(b, 128, 32, n, 27, in->h_bias[0][n]);
+    }
+    nc++;
+  }
+  for (int l = 1; l < 6; ++l) {
+    const int O = in->out_dim[l], I = in->in_dim[l];
+    for (int c = 0; c < 5; ++c) {
+      const size_t b = add_chunk(128, 32);
+      for (int n = 0; n < O && n < 128; ++n)
+        for (int kk = 0; kk < 32; ++kk) {
+          const int k = c * 32 + kk;
+          if (k < I) put(b, 128, 32, n, kk, W[l][(size_t)n * I + k]);
+          else if (k == 156) put(b, 128, 32, n, kk, in->h_bias[l][n]);
+        }
+      nc++;
+    }
+  }
+  S.n_fwd = nc;
+  // reverse lin5..lin1: B[n = input index (160 rows)][k = output index], 4 chunks of K = 32
+  for (int l = 5; l >= 1; --l) {
+    const int O = in->out_dim[l], I = in->in_dim[l];
+    for (int c = 0; c < 4; ++c) {
+      const size_t b = add_chunk(160, 32);
+      for (int kk = 0; kk < 32; ++kk) {
+        const int k = c * 32 + kk;
+        if (k >= O) continue;
+        for (int n = 0; n < I && n < 160; ++n) put(b, 160, 32, n, kk, W[l][(size_t)k * I + n]);
+      }
+      nc++;
+    }
+  }
+  // reverse lin0: B[n = PE index (32 rows)][k = output index], 2 chunks of K = 64
+  {
+    const int O = in->out_dim[0], I = in->in_dim[0];
+    for (int c = 0; c < 2; ++c) {
+      const size_t b = add_chunk(32, 64);
+      for (int kk = 0; kk < 64; ++kk) {
+        const int k = c * 64 + kk;
+        if (k >= O) continue;
+        for (int n = 0; n < I && n < 32; ++n) put(b, 32, 64, n, kk, W[0][(size_t)k * I + n]);
+      }
+      nc++;
+    }
+  }
+  S.n_all = nc;
+  void* p = nullptr;
+  int rc = dev_alloc(net, &p, blob.size() * 2);
+  if (rc) return rc;
+  SURF_CUDA(cudaMemcpyAsync(p, blob.data(), blob.size() * 2, cudaMemcpyHostToDevice, st));
+  SURF_CUDA(cudaStreamSynchronize(st));
+  net->tc1_blob = (const uint8_t*)p;
+  // softplus' scratch: 5 layers x 4 x 512 threads x 16 B per CTA
+  rc = dev_alloc(net, &p, (size_t)net->n_sm * 5 * 4 * T1_EPI_THREADS * sizeof(uint4));
+  if (rc) return rc;
+  net->tc1_scratch = p;
+  return 0;
+}
+
+int launch_sdf_tc1(const surf_scene* s, const surf_net* n, const PointSource& src, float* d_sdf, float* d_grad,
+                   bool negate, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    SURF_CUDA(cudaFuncSetAttribute(k_sdf_tc1<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, S1_TOTAL));
+    SURF_CUDA(cudaFuncSetAttribute(k_sdf_tc1<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, S1_TOTAL));
+    attr_set = true;
+  }
+  if (src.n <= 0) return 0;
+  const int64_t tiles = (src.n + 127) / 128;
+  const int grid = (int)(tiles < n->n_sm ? tiles : n->n_sm);
+  surf_time_begin(d_grad ? 0 : 1, st);
+  if (d_grad) {
+    k_sdf_tc1<true><<<grid, T1_THREADS, S1_TOTAL, st>>>(s->dev, n->dev, src, n->tc1_blob, g_t1_stream, d_sdf, d_grad,
+                                                        (uint4*)n->tc1_scratch, negate ? 1 : 0);
+  } else {
+    k_sdf_tc1<false><<<grid, T1_THREADS, S1_TOTAL, st>>>(s->dev, n->dev, src, n->tc1_blob, g_t1_stream, d_sdf, nullptr,
+                                                         (uint4*)n->tc1_scratch, negate ? 1 : 0);
+  }
+  surf_time_end(d_grad ? 0 : 1, st);
+  SURF_LAUNCH_CHECK();
+  return 0;
+}

@@ -78,3 +78,66 @@ def test_tc_sdf_grid_vs_reference(tc_mode):
     assert_close(u, g["out"]["u"], RTOL_FP32, "tensor-core u grid vs reference golden")
     wild = g["in"]["wild_pts"].cuda()
     assert_close(m.sdf_network.sdf(wild, ps), g["out"]["wild_full"][:, :1], RTOL_FP32, "tc sdf, out-of-range points")
+
+
+# ------------------------------------------------------------------------------------------------
+# one-tile tensor-core kernel: forward + analytic gradient
+# ------------------------------------------------------------------------------------------------
+def _setup(name):
+    g = load_golden(name)
+    sc = scene_from_recipe(g["recipe"])
+    m = ImplicitSurface(conf.default_implicit_surface_conf())
+    m.load_state_dict(g["sd"])
+    m = m.cuda()
+    d = sc.to("cuda")
+    ps = m.prepare(d.matching_volume, d.volumes, d.sparse_idxes, d.mask_volumes, d.imgs, d.features, d.intrs, d.c2ws)
+    return g, sc, d, m, ps
+
+
+@pytest.mark.parametrize("name", ["render_v2_perturbed", "render_v2_init", "render_v4_perturbed"])
+def test_tc_gradient_vs_reference(name, tc_mode):
+    g, sc, d, m, ps = _setup(name)
+    pv = torch.from_numpy(g["out"]["_pts_valid"]).cuda()
+    sdf, grad = m.sdf_network.gradient(pv, ps, with_sdf=True)
+    assert_close(sdf, g["out"]["_sdf_full"][:, :1], RTOL_FP32, "tc sdf (gradient kernel) vs reference golden")
+    assert_close(grad, g["out"]["_grad_valid"], RTOL_FP32, "tc d sdf / d x vs reference autograd")
+    s2, g2 = m.sdf_network.gradient(pv, ps, with_sdf=True)
+    assert torch.equal(sdf, s2) and torch.equal(grad, g2), "tensor-core gradient kernel must be deterministic"
+    for n in (1, 127, 129, 300):
+        s3, g3 = m.sdf_network.gradient(pv[:n], ps, with_sdf=True)
+        assert torch.equal(s3, sdf[:n]) and torch.equal(g3, grad[:n])
+    _lib.set_mlp_mode(3)
+    assert_close(m.sdf_network.sdf(pv, ps), g["out"]["_sdf_full"][:, :1], RTOL_FP32, "tc1 forward-only sdf")
+
+
+def test_tc_gradient_wild_points(tc_mode):
+    g, sc, d, m, ps = _setup("sdf_grid_24")
+    wild = g["in"]["wild_pts"].cuda()
+    s, gr = m.sdf_network.gradient(wild, ps, with_sdf=True)
+    assert_close(s, g["out"]["wild_full"][:, :1], RTOL_FP32, "tc sdf, out-of-range points")
+    assert_close(gr, g["out"]["wild_grad"], RTOL_FP32, "tc gradient, out-of-range points")
+
+
+@pytest.mark.parametrize("name", ["render_v2_perturbed", "render_v2_init", "render_v4_perturbed", "render_miss"])
+def test_tc_render_end_to_end(name, tc_mode):
+    import surf_oracle as O
+    from helpers import assert_equal_int
+    g, sc, d, m, ps = _setup(name)
+    i = g["in"]
+    torch.manual_seed(int(g["recipe"]["torch_seed"]))
+    t_rand = O.draw_t_rand(i["rays_o"].shape[0], 4)
+    pts_random = torch.rand(1024, 3) * 2 - 1
+    out = m.render(i["rays_o"].cuda(), i["rays_d"].cuda(), i["near"].cuda(), i["far"].cuda(), ps, None, None, None, None,
+                   None, None, None, None, 1.0, None, t_rand=t_rand, pts_random=pts_random, return_stages=True)
+    net = O.OracleNet(g["sd"])
+    ref = O.render(net, i["rays_o"], i["rays_d"], i["near"], i["far"], sc.matching_volume, sc.volumes, sc.sparse_idxes,
+                   sc.mask_volumes, sc.imgs, sc.features, sc.intrs, sc.c2ws, 1.0, t_rand=t_rand, pts_random=pts_random,
+                   return_stages=True)
+    mism = int(((out["_point_flags"].cpu() & 1).bool() != ref["_voxel_mask"]).sum())
+    assert mism <= 2
+    assert_close(out["gradients"], ref["gradients"], RTOL_FP32, "gradients")
+    assert_close(out["sparse_sdf"], ref["sparse_sdf"], RTOL_FP32, "sparse_sdf")
+    if mism == 0 and name != "render_v4_perturbed":
+        for k in ("color_fine", "render_depth", "sdf_depth", "normal", "weight_sum"):
+            assert_close(out[k], ref[k], 5e-4, k, floor=1e-2)
+        assert_equal_int(out["valid_mask"], ref["valid_mask"], "valid_mask")
