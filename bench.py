@@ -360,13 +360,19 @@ def run_gpu(args):
             traffic = json.load(open(prof_json)).get("sdf_mlp_grad", {}).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roofline = {"kernel": "k_sdf_mlp<GRAD=true> (sparse gather + SDF MLP forward + input gradient)", "bound": "tensor",
+    tc = args.mlp_mode >= 1
+    kname = ("k_sdf_tc1<GRAD=true> (tcgen05: sparse gather + SDF MLP forward + input gradient, fp16 hi/lo 3-MMA)" if tc
+             else "k_sdf_mlp<GRAD=true> (fp32 FFMA: sparse gather + SDF MLP forward + input gradient)")
+    roofline = {"kernel": kname, "bound": "tensor",
                 "achieved": achieved_tflops, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
                 "frac": achieved_tflops / pk["bf16_tflops"], "traffic": traffic, "peak_source": pk_src,
                 "algorithmic": "%d evaluated points/step x %d FLOP (fwd+input-grad, SURVEY 8d) over %d launches/step"
                                % (n_eval, FLOP_PER_POINT_FWD_BWD, mlp_launches // n_prof),
-                "note": "fp32 FFMA edition of the MLP (no tensor-core path yet): fraction is against the measured "
-                        "bf16 tensor peak", "kernel_ms_per_step": kernel_share}
+                "note": ("achieved counts ALGORITHMIC flops (one fp32 product each); the fp32-parity mode issues every "
+                         "product as 3 fp16 MMAs (hi*hi + lo*hi + hi*lo), so the tensor pipe executes 3x this figure"
+                         if tc else "fp32 FFMA edition of the MLP: fraction is against the measured bf16 tensor peak"),
+                "tensor_work_tflops": achieved_tflops * (3.0 if tc else 0.0),
+                "kernel_ms_per_step": kernel_share}
 
     # ---- e2e through the public API with host buffers -------------------------------------------------
     for _ in range(2):
@@ -394,8 +400,9 @@ def run_gpu(args):
         line = {
             "metric": "rays_per_sec", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-            "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": config_dict(args, world, {"voxels_fine_to_coarse": voxels, "evaluated_points_per_step": n_eval,
+            "scaling": "strong" if strong else "weak", "vs_baseline": None,
+            "dtype": "f32 (tcgen05 fp16 hi/lo split, fp32 accumulate)" if tc else "f32", "data": "synthetic",
+            "config": config_dict(args, world, {"voxels_fine_to_coarse": voxels, "evaluated_points_per_step": n_eval, "mlp_mode": args.mlp_mode,
                                                 "scene_prepare_s": prepare_s, "scene_bytes": stats}),
             "clocks": clock_info, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),

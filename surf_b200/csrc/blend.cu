@@ -537,6 +537,8 @@ int launch_blend(const surf_scene*, const surf_net* n, const float* d_feat, cons
   }
   if (n_pts <= 0) return 0;
   SURF_CHECK_ARG(V >= 1 && V <= SURF_MAX_VIEWS, "n_src_views");
+  if (surf_mlp_mode() >= 1)
+    return launch_blend_tc(n, d_feat, d_raydiff, d_mask, V, packed19, list, count, n_pts, d_rgb, d_views, st);
   const int ppt = BL_ROWS / V;
   int64_t tiles = (n_pts + ppt - 1) / ppt;
   const int grid = (int)(tiles < n->n_sm ? tiles : n->n_sm);

@@ -10,6 +10,8 @@ int surf_build_sdf_weights(const surf_net_inputs* in, surf_net* net, cudaStream_
                            int (*dev_alloc)(surf_net*, void**, size_t));
 int surf_build_blend_weights(const surf_net_inputs* in, surf_net* net, cudaStream_t st,
                              int (*dev_alloc)(surf_net*, void**, size_t));
+int surf_build_blend_tc_weights(const surf_net_inputs* in, surf_net* net, cudaStream_t st,
+                                int (*dev_alloc)(surf_net*, void**, size_t));
 int surf_flags_pass(const surf_scene* s, const surf_render_cfg* cfg, const float* d_rays_o, const float* d_rays_d,
                     const float* d_z_vals, int64_t B, int S, float* d_mid, uint8_t* d_flags, float* d_sdf,
                     float* d_grad, int32_t* d_list, int32_t* d_counter, int32_t* d_chunk_any, int n_chunks,
@@ -342,6 +344,7 @@ extern "C" int surf_net_create(const surf_net_inputs* in, void* stream, surf_net
   n->n_sm = surf_num_sms();
   int rc = surf_build_sdf_weights(in, n, st, net_alloc);
   if (rc == 0) rc = surf_build_blend_weights(in, n, st, net_alloc);
+  if (rc == 0) rc = surf_build_blend_tc_weights(in, n, st, net_alloc);
   if (rc == 0) {
     n->scratch_bytes = (size_t)n->n_sm * 6 * 16 * MLP_THREADS * sizeof(float4);
     void* p = nullptr;

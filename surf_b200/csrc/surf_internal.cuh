@@ -81,6 +81,8 @@ struct surf_net {
   const uint8_t* tc_blob;           // tensor-core weight stream (fp16 hi/lo chunks, sdf_tc.cu)
   const uint8_t* tc1_blob;          // forward + reverse weight stream of sdf_tc1.cu
   void* tc1_scratch;                // softplus' scratch (unorm16) of sdf_tc1.cu
+  const uint8_t* blend_tc_w;        // blend_tc.cu: fp16 hi/lo tensor-core operands
+  const float* blend_tc_f;          // blend_tc.cu: fp32 small-layer weights and biases
   int tc_ok;                        // network shape supported by the tensor-core kernels
   float* scratch;                   // sigma' scratch for the backward pass (per-CTA private)
   size_t scratch_bytes;
@@ -254,6 +256,9 @@ int launch_sdf_tc_fwd(const surf_scene* s, const surf_net* n, const PointSource&
                       cudaStream_t st);
 int launch_sdf_tc1(const surf_scene* s, const surf_net* n, const PointSource& src, float* d_sdf, float* d_grad,
                    bool negate, cudaStream_t st);
+int launch_blend_tc(const surf_net* n, const float* d_feat, const float* d_raydiff, const uint8_t* d_mask, int V,
+                    bool packed19, const int32_t* list, const int32_t* count, int64_t n_pts, float* d_rgb,
+                    uint8_t* d_views, cudaStream_t st);
 int surf_mlp_mode();   // 0 = fp32 FFMA kernels, 1 = tcgen05 kernels (fp16 hi/lo split, fp32-grade)
 int launch_lookup_feature(const surf_scene* s, const PointSource& src, float* d_feat, float* d_raydiff,
                           uint8_t* d_mask, bool packed19, cudaStream_t st);

@@ -141,3 +141,28 @@ def test_tc_render_end_to_end(name, tc_mode):
         for k in ("color_fine", "render_depth", "sdf_depth", "normal", "weight_sum"):
             assert_close(out[k], ref[k], 5e-4, k, floor=1e-2)
         assert_equal_int(out["valid_mask"], ref["valid_mask"], "valid_mask")
+
+
+@pytest.mark.parametrize("name", ["render_v2_perturbed", "render_v2_init", "render_v4_perturbed"])
+def test_tc_blend_vs_reference(name, tc_mode):
+    import surf_oracle as O
+    from helpers import blend_envelope
+    g = load_golden(name)
+    m = ImplicitSurface(conf.default_implicit_surface_conf())
+    m.load_state_dict(g["sd"])
+    m = m.cuda()
+    o = g["out"]
+    net = O.OracleNet(g["sd"])
+    fv, rd, mk = (torch.from_numpy(o[k]) for k in ("_feat_views", "_ray_diff", "_view_mask"))
+    got = m.color_network(fv.cuda(), rd.cuda(), mk.cuda()).cpu()
+    ref = torch.from_numpy(o["_blend_rgb"])
+    _, env = blend_envelope(O, net, fv, rd, mk)
+    err = (got - ref).abs().max(dim=1)[0]
+    tol = RTOL_FP32 * float(ref.abs().max()) + 2.0 * env
+    assert bool((err <= tol).all()), "tc blend rgb: %d/%d points beyond 1e-4 + envelope (max err %.3e)" % (
+        int((err > tol).sum()), err.numel(), float(err.max()))
+    mk0 = torch.zeros_like(mk)
+    assert_close(m.color_network(fv.cuda(), rd.cuda(), mk0.cuda()), O.blend(net, fv, rd, mk0), RTOL_FP32,
+                 "tc blend rgb, nothing visible")
+    again = m.color_network(fv.cuda(), rd.cuda(), mk.cuda()).cpu()
+    assert torch.equal(got, again)
