@@ -40,6 +40,20 @@
 #define S1_BAR (S1_GF + 14336)
 #define S1_TOTAL (S1_BAR + 256)
 
+#ifdef TC_TRACE
+__device__ long long g_t1_trace[8192];
+__device__ int g_t1_trace_n;
+#define TRACE1(ev)                                                                 \
+  do {                                                                             \
+    if (blockIdx.x == 0 && lane == 0) {                                            \
+      const int _i = atomicAdd(&g_t1_trace_n, 1);                                  \
+      if (_i < 4096) { g_t1_trace[2 * _i] = (ev); g_t1_trace[2 * _i + 1] = clock64(); } \
+    }                                                                              \
+  } while (0)
+#else
+#define TRACE1(ev) do {} while (0)
+#endif
+
 struct T1Stream {
   int n_fwd, n_all;
   uint32_t off[T1_MAXCHUNK];      // byte offset in the blob
@@ -153,29 +167,31 @@ k_sdf_tc1(const DevScene sc, const DevNet net, const PointSource src, const uint
              __half2float(*reinterpret_cast<const __half*>(base + 8192 + off));
     };
     auto epi_bar = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(T1_EPI_THREADS) : "memory"); };
+    auto load_point = [&](int64_t i, float& px, float& py, float& pz) -> int64_t {
+      px = 0.f; py = 0.f; pz = 0.f;
+      if (i >= n_total) return -1;
+      const int64_t id = src.list ? (int64_t)src.list[i] : i;
+      if (src.mode == 0) {
+        px = src.pts[id * 3]; py = src.pts[id * 3 + 1]; pz = src.pts[id * 3 + 2];
+      } else if (src.mode == 1) {
+        const int64_t ray = id / src.S;
+        const float t = src.mid_z[id];
+        px = ray_at(src.rays_o[ray * 3], src.rays_d[ray * 3], t);
+        py = ray_at(src.rays_o[ray * 3 + 1], src.rays_d[ray * 3 + 1], t);
+        pz = ray_at(src.rays_o[ray * 3 + 2], src.rays_d[ray * 3 + 2], t);
+      } else {
+        const int64_t yz = (int64_t)src.ny * src.nz;
+        const int xi = (int)(id / yz);
+        const int rem = (int)(id - (int64_t)xi * yz);
+        px = src.xs[xi]; py = src.ys[rem / src.nz]; pz = src.zs[rem % src.nz];
+      }
+      return id;
+    };
 
     for (int64_t it = 0; it < my_tiles; ++it) {
       const int64_t tile = (int64_t)blockIdx.x + it * gridDim.x;
-      const int64_t i = tile * 128 + r;
-      float px = 0.f, py = 0.f, pz = 0.f;
-      int64_t id = -1;
-      if (i < n_total) {
-        id = src.list ? (int64_t)src.list[i] : i;
-        if (src.mode == 0) {
-          px = src.pts[id * 3]; py = src.pts[id * 3 + 1]; pz = src.pts[id * 3 + 2];
-        } else if (src.mode == 1) {
-          const int64_t ray = id / src.S;
-          const float t = src.mid_z[id];
-          px = ray_at(src.rays_o[ray * 3], src.rays_d[ray * 3], t);
-          py = ray_at(src.rays_o[ray * 3 + 1], src.rays_d[ray * 3 + 1], t);
-          pz = ray_at(src.rays_o[ray * 3 + 2], src.rays_d[ray * 3 + 2], t);
-        } else {
-          const int64_t yz = (int64_t)src.ny * src.nz;
-          const int xi = (int)(id / yz);
-          const int rem = (int)(id - (int64_t)xi * yz);
-          px = src.xs[xi]; py = src.ys[rem / src.nz]; pz = src.zs[rem % src.nz];
-        }
-      }
+      float px, py, pz;
+      const int64_t id = load_point(tile * 128 + r, px, py, pz);
       // ---- staging: thread (row, part) gathers level `part` and encodes PE frequency `part` ----
       {
         float f7[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -207,13 +223,20 @@ k_sdf_tc1(const DevScene sc, const DevNet net, const PointSource src, const uint
       tc::fence_proxy_async();
       tc::tc_fence_before();
       tc::mbar_arrive(&bars->a_ready);
+      if (warp == 0) TRACE1(1);
 
       float gf[8];          // reverse pass: d sdf / d feat for feature columns part*8 .. part*8+7
       // ------------------------------------ forward ------------------------------------
       for (int l = 0; l < 6; ++l) {
+        if (l == 1 && it + 1 < my_tiles && part < sc.n_levels) {
+          // while the tensor core works on this layer: pull the NEXT tile's gather working set into L2
+          float nx, ny, nz;
+          if (load_point((tile + gridDim.x) * 128 + r, nx, ny, nz) >= 0) sparse_prefetch_l2(sc, part, nx, ny, nz);
+        }
         tc::mbar_wait(&bars->d_full, ph_d & 1);
         ph_d++;
         tc::tc_fence_after();
+        if (warp == 0) TRACE1(10 + l);
         const bool to_skip = (l + 1 == net.skip_layer);
         float head = 0.f;
         uint32_t sp[16];      // softplus' of my 32 columns as unorm16 pairs
@@ -262,6 +285,7 @@ k_sdf_tc1(const DevScene sc, const DevNet net, const PointSource src, const uint
           tc::tmem_wait_st();
           tc::tc_fence_before();
           tc::mbar_arrive(&bars->a_ready);
+          if (warp == 0) TRACE1(30 + l);
         }
         if (GRAD && l < 5) {
 #pragma unroll
@@ -297,6 +321,7 @@ k_sdf_tc1(const DevScene sc, const DevNet net, const PointSource src, const uint
         tc::mbar_wait(&bars->d_full, ph_d & 1);
         ph_d++;
         tc::tc_fence_after();
+        if (warp == 0) TRACE1(16 + (5 - l));
         const uint32_t* spw = reinterpret_cast<const uint32_t*>(spv);
         const bool is_skip = (l == net.skip_layer);
 #pragma unroll
@@ -338,6 +363,7 @@ k_sdf_tc1(const DevScene sc, const DevNet net, const PointSource src, const uint
         tc::tmem_wait_st();
         tc::tc_fence_before();
         tc::mbar_arrive(&bars->a_ready);
+        if (warp == 0) TRACE1(36 + (5 - l));
       }
       // feature gradients -> smem (28 x 128)
 #pragma unroll
@@ -392,6 +418,7 @@ k_sdf_tc1(const DevScene sc, const DevNet net, const PointSource src, const uint
         grad_out[id * 3 + d] = gx;
       }
       epi_bar();                                   // smem scratch free for the next tile
+      if (warp == 0) TRACE1(99);
     }
   } else if (warp < T1_EPI_WARPS + 2) {
     // =============================== MMA issuers: sub 0 -> D_a, sub 1 -> D_b ===============================
@@ -414,6 +441,7 @@ k_sdf_tc1(const DevScene sc, const DevNet net, const PointSource src, const uint
           tc::mbar_wait(&bars->a_ready, ph_a & 1);
           ph_a++;
           tc::tc_fence_after();
+          if (sub == 0) TRACE1(50 + p);
           for (int c = 0; c < nch; ++c, ++s) {
             if ((c & 1) != sub) continue;
             const int slot = (int)(s % T1_NSLOT);
@@ -464,6 +492,7 @@ k_sdf_tc1(const DevScene sc, const DevNet net, const PointSource src, const uint
             tc::mma_commit(&bars->w_empty[slot]);
           }
           tc::mma_commit(&bars->d_full);
+          if (sub == 0) TRACE1(70 + p);
         }
       }
     }
@@ -611,3 +640,16 @@ int launch_sdf_tc1(const surf_scene* s, const surf_net* n, const PointSource& sr
   SURF_LAUNCH_CHECK();
   return 0;
 }
+
+#ifdef TC_TRACE
+extern "C" int surf_t1_trace_read(long long* h_out, int max_events) {
+  int n = 0;
+  cudaMemcpyFromSymbol(&n, g_t1_trace_n, sizeof(int));
+  if (n > max_events) n = max_events;
+  if (n > 4096) n = 4096;
+  cudaMemcpyFromSymbol(h_out, g_t1_trace, sizeof(long long) * 2 * n);
+  int zero = 0;
+  cudaMemcpyToSymbol(g_t1_trace_n, &zero, sizeof(int));
+  return n;
+}
+#endif

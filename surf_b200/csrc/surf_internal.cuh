@@ -221,6 +221,34 @@ __device__ __forceinline__ void sparse_level(const DevScene& sc, int l, float px
   }
 }
 
+// L2 prefetch of everything sparse_level will touch for this point: the 8 index entries are loaded (blocking),
+// then the (up to) 8 voxel rows are requested with prefetch.global.L2.  Used to pull the next tile's gather
+// working set into L2 while the current tile is busy on the tensor core.
+__device__ __forceinline__ void sparse_prefetch_l2(const DevScene& sc, int l, float px, float py, float pz) {
+  const int N = sc.dim[l];
+  const float vs = sc.voxel[l];
+  const float fx0 = floorf(__fdiv_rn(__fadd_rn(pz, 1.0f), vs));
+  const float fy0 = floorf(__fdiv_rn(__fadd_rn(py, 1.0f), vs));
+  const float fz0 = floorf(__fdiv_rn(__fadd_rn(px, 1.0f), vs));
+  const float hi = (float)(N - 1);
+  const int x0 = (int)fminf(fmaxf(fx0, 0.f), hi), x1 = (int)fminf(fmaxf(fx0 + 1.0f, 0.f), hi);
+  const int y0 = (int)fminf(fmaxf(fy0, 0.f), hi), y1 = (int)fminf(fmaxf(fy0 + 1.0f, 0.f), hi);
+  const int z0 = (int)fminf(fmaxf(fz0, 0.f), hi), z1 = (int)fminf(fmaxf(fz0 + 1.0f, 0.f), hi);
+  const int32_t* __restrict__ idx = sc.index[l];
+  int32_t rows[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const int xi = (c & 1) ? x1 : x0, yi = (c & 2) ? y1 : y0, zi = (c & 4) ? z1 : z0;
+    rows[c] = __ldg(idx + ((size_t)zi * N + yi) * N + xi);
+  }
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    if (rows[c] < 0) continue;
+    const float4* p = sc.vol8[l] + (size_t)rows[c] * 2;
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+  }
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
