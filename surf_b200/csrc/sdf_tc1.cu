@@ -83,24 +83,139 @@ __device__ __forceinline__ float t1_rcp(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// softplus(beta=100) and its derivative sigmoid(100 z), branch-free (see sdf_tc.cu)
-template <bool GRAD>
-__device__ __forceinline__ float t1_softplus(float z, float& dh) {
+// softplus(beta=100), branch-free (see sdf_tc.cu).  For the reverse pass the forward epilogue parks
+// u = 1 + exp(-|100 z|) (16 mantissa bits, no int conversion: F2I / I2F / RCP all run on the quarter-rate XU
+// pipe that already carries ex2 + lg2) plus the sign of z; softplus'(z) = sigmoid(100 z) = z >= 0 ? 1/u : 1 - 1/u
+// is formed in the reverse epilogue.
+__device__ __forceinline__ float t1_softplus(float z, float& u) {
   const float e = t1_ex2(fabsf(z) * -144.26950408889634f);
-  const float u = 1.0f + e;
-  if (GRAD) {
-    const float r = t1_rcp(u);
-    dh = (z >= 0.f) ? r : 1.0f - r;
-  }
+  u = 1.0f + e;
   return fmaf(t1_lg2(u), 0.0069314718055994531f, fmaxf(z, 0.f));
 }
+// u in [1,2] -> 16 bit code (round to nearest of the top 16 mantissa bits; 2.0 saturates) and back
+__device__ __forceinline__ uint32_t t1_pack_u(float u) {
+  // + 2^-17 (half a code step); genuine values saturate at code 0xfffe, 0xffff (+ sign) is reserved for PE columns
+  const float c = fminf(u + 7.62939453125e-06f, 1.99997711181640625f);
+  return (__float_as_uint(c) >> 7) & 0xffffu;
+}
+__device__ __forceinline__ float t1_unpack_u(uint32_t code) { return __uint_as_float(0x3f800000u | (code << 7)); }
 
 // chunk layout per layer phase of the weight stream
 __device__ __forceinline__ int t1_phase_chunks(int phase) {   // phases 0..5 fwd, 6..10 reverse lin5..lin1, 11 reverse lin0
   if (phase == 0) return 1;
-  if (phase < 6) return 5;
+  if (phase < 6) return 6;      // 4 x K32 hidden + 2 x K16 (features | bias)
   if (phase < 11) return 4;
   return 2;
+}
+
+struct EpiCtx {
+  uint32_t tl;            // TMEM base of my lane quarter
+  int c0, r, te;
+  const uint8_t* ape;
+  const float* sw6;
+  float inv_scale;
+  uint4* scratch;
+  uint32_t* sgn_scratch;
+  float* s_gpe;
+};
+
+__device__ __forceinline__ float t1_get_k(const uint8_t* base, int r, int k) {
+  const uint32_t off = (uint32_t)(k >> 3) * 2048u + r * 16 + (k & 7) * 2;
+  return __half2float(*reinterpret_cast<const __half*>(base + off)) +
+         __half2float(*reinterpret_cast<const __half*>(base + 8192 + off));
+}
+
+// Forward epilogue of one hidden layer for my 32 columns.  HAS_B: a second accumulator exists (every layer but lin0);
+// SKIP: my columns 101..127 become the positional encoding (input of the skip layer); HEAD: lin5 -> SDF head partial
+// sum and (GRAD) delta5 = w6 / scale * softplus' written back as the first reverse A operand.
+template <bool GRAD, bool HAS_B, bool SKIP, bool HEAD>
+__device__ __forceinline__ void t1_fwd_epilogue(const EpiCtx& c, int l, float& head) {
+  uint32_t sp[16];
+  uint32_t sgn = 0;
+#pragma unroll
+  for (int hb = 0; hb < 2; ++hb) {
+    const int cb = c.c0 + hb * 16;
+    uint32_t a[16], b[16];
+    tc::tmem_ld16(c.tl + T1_DA + cb, a);
+    if (HAS_B) tc::tmem_ld16(c.tl + T1_DB + cb, b);
+    tc::tmem_wait_ld();
+    uint32_t hi[8], lo[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float z0 = __uint_as_float(a[2 * j]), z1 = __uint_as_float(a[2 * j + 1]);
+      if (HAS_B) {
+        z0 += __uint_as_float(b[2 * j]);
+        z1 += __uint_as_float(b[2 * j + 1]);
+      }
+      float u0, u1;
+      float h0 = t1_softplus(z0, u0);
+      float h1 = t1_softplus(z1, u1);
+      const int n0 = hb * 16 + 2 * j;                       // column offset inside my 32 (compile time)
+      const bool pe0 = SKIP && (96 + n0 >= 101), pe1 = SKIP && (96 + n0 + 1 >= 101);   // SKIP => c0 == 96
+      if (pe0) h0 = t1_get_k(c.ape, c.r, 96 + n0 - 101);
+      if (pe1) h1 = t1_get_k(c.ape, c.r, 96 + n0 + 1 - 101);
+      if (HEAD) {
+        const float w0 = c.sw6[c.c0 + n0], w1 = c.sw6[c.c0 + n0 + 1];
+        head = fmaf(h0, w0, head);
+        head = fmaf(h1, w1, head);
+        if (GRAD) {
+          const float r0 = t1_rcp(u0), r1 = t1_rcp(u1);
+          h0 = w0 * c.inv_scale * (z0 >= 0.f ? r0 : 1.0f - r0);
+          h1 = w1 * c.inv_scale * (z1 >= 0.f ? r1 : 1.0f - r1);
+        }
+      } else if (GRAD) {
+        // 16-bit code of u = 1 + exp(-|100 z|) and the sign of z; PE columns: reserved code 0xffff + sign set
+        const uint32_t q0 = pe0 ? 0xffffu : t1_pack_u(u0), q1 = pe1 ? 0xffffu : t1_pack_u(u1);
+        sp[hb * 8 + j] = q0 | (q1 << 16);
+        if (pe0) sgn |= 1u << n0; else sgn |= (__float_as_uint(z0) >> 31) << n0;
+        if (pe1) sgn |= 1u << (n0 + 1); else sgn |= (__float_as_uint(z1) >> 31) << (n0 + 1);
+      }
+      tc::split2(h0, h1, hi[j], lo[j]);
+    }
+    if (!HEAD || GRAD) {
+      tc::tmem_st8(c.tl + T1_AHI + (cb >> 1), hi);
+      tc::tmem_st8(c.tl + T1_ALO + (cb >> 1), lo);
+    }
+  }
+  if (GRAD && !HEAD) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      c.scratch[(size_t)(l * 4 + j) * T1_EPI_THREADS + c.te] = make_uint4(sp[4 * j], sp[4 * j + 1], sp[4 * j + 2], sp[4 * j + 3]);
+    c.sgn_scratch[(size_t)l * T1_EPI_THREADS + c.te] = sgn;
+  }
+}
+
+// Reverse epilogue: delta_{l-1} = (D_a + D_b) * softplus'(z_{l-1}) for my 32 columns -> next A operand.
+// SKIP_PE: this is the skip layer and my columns 101..127 are the PE input gradient (kept in smem, delta = 0).
+template <bool SKIP_PE>
+__device__ __forceinline__ void t1_bwd_epilogue(const EpiCtx& c, const uint4 (&spv)[4], uint32_t sgn) {
+  const uint32_t* spw = reinterpret_cast<const uint32_t*>(spv);
+#pragma unroll
+  for (int hb = 0; hb < 2; ++hb) {
+    const int cb = c.c0 + hb * 16;
+    uint32_t a[16], b[16];
+    tc::tmem_ld16(c.tl + T1_DA + cb, a);
+    tc::tmem_ld16(c.tl + T1_DB + cb, b);
+    tc::tmem_wait_ld();
+    uint32_t hi[8], lo[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float g0 = __uint_as_float(a[2 * j]) + __uint_as_float(b[2 * j]);
+      const float g1 = __uint_as_float(a[2 * j + 1]) + __uint_as_float(b[2 * j + 1]);
+      const int n0 = hb * 16 + 2 * j;
+      const uint32_t w = spw[hb * 8 + j];
+      const float r0 = t1_rcp(t1_unpack_u(w & 0xffffu)), r1 = t1_rcp(t1_unpack_u(w >> 16));
+      float d0 = ((sgn >> n0) & 1u) ? 1.0f - r0 : r0;
+      float d1 = ((sgn >> (n0 + 1)) & 1u) ? 1.0f - r1 : r1;
+      if (SKIP_PE) {                                        // c0 == 96
+        if (96 + n0 >= 101) { c.s_gpe[(96 + n0 - 101) * 128 + c.r] = g0; d0 = 0.f; }
+        if (96 + n0 + 1 >= 101) { c.s_gpe[(96 + n0 + 1 - 101) * 128 + c.r] = g1; d1 = 0.f; }
+      }
+      tc::split2(g0 * d0, g1 * d1, hi[j], lo[j]);
+    }
+    tc::tmem_st8(c.tl + T1_AHI + (cb >> 1), hi);
+    tc::tmem_st8(c.tl + T1_ALO + (cb >> 1), lo);
+  }
 }
 
 template <bool GRAD>
@@ -151,7 +266,8 @@ k_sdf_tc1(const DevScene sc, const DevNet net, const PointSource src, const uint
     float* s_part = reinterpret_cast<float*>(smem + S1_PART);
     float* s_gpe = reinterpret_cast<float*>(smem + S1_GPE);
     float* s_gf = reinterpret_cast<float*>(smem + S1_GF);
-    uint4* scratch = scratch_all + (size_t)blockIdx.x * (5 * 4 * T1_EPI_THREADS);
+    uint4* scratch = scratch_all + (size_t)blockIdx.x * (5 * 4 * T1_EPI_THREADS + 5 * T1_EPI_THREADS / 4);
+    uint32_t* sgn_scratch = reinterpret_cast<uint32_t*>(scratch + 5 * 4 * T1_EPI_THREADS);
     const int te = warp * 32 + lane;             // 0..511
     uint32_t ph_d = 0;
     auto put_k = [&](uint8_t* base, int k, float v) {
@@ -188,6 +304,8 @@ k_sdf_tc1(const DevScene sc, const DevNet net, const PointSource src, const uint
       return id;
     };
 
+    float nf7[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // next tile's features of (row, level = part), gathered early
+    bool have_next = false;
     for (int64_t it = 0; it < my_tiles; ++it) {
       const int64_t tile = (int64_t)blockIdx.x + it * gridDim.x;
       float px, py, pz;
@@ -195,7 +313,12 @@ k_sdf_tc1(const DevScene sc, const DevNet net, const PointSource src, const uint
       // ---- staging: thread (row, part) gathers level `part` and encodes PE frequency `part` ----
       {
         float f7[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        if (part < sc.n_levels) sparse_level<0>(sc, part, px, py, pz, nullptr, f7);
+        if (GRAD && have_next) {
+#pragma unroll
+          for (int c = 0; c < 7; ++c) f7[c] = nf7[c];
+        } else if (part < sc.n_levels) {
+          sparse_level<0>(sc, part, px, py, pz, nullptr, f7);
+        }
 #pragma unroll
         for (int c = 0; c < 7; ++c) put_k(afeat, part * 7 + c, f7[c]);
         const float xs[3] = {px * net.scale, py * net.scale, pz * net.scale};
@@ -227,6 +350,9 @@ k_sdf_tc1(const DevScene sc, const DevNet net, const PointSource src, const uint
 
       float gf[8];          // reverse pass: d sdf / d feat for feature columns part*8 .. part*8+7
       // ------------------------------------ forward ------------------------------------
+      EpiCtx ec;
+      ec.tl = tl; ec.c0 = c0; ec.r = r; ec.te = te; ec.ape = ape; ec.sw6 = sw6; ec.inv_scale = net.inv_scale;
+      ec.scratch = scratch; ec.sgn_scratch = sgn_scratch; ec.s_gpe = s_gpe;
       for (int l = 0; l < 6; ++l) {
         if (l == 1 && it + 1 < my_tiles && part < sc.n_levels) {
           // while the tensor core works on this layer: pull the NEXT tile's gather working set into L2
@@ -237,60 +363,17 @@ k_sdf_tc1(const DevScene sc, const DevNet net, const PointSource src, const uint
         ph_d++;
         tc::tc_fence_after();
         if (warp == 0) TRACE1(10 + l);
-        const bool to_skip = (l + 1 == net.skip_layer);
         float head = 0.f;
-        uint32_t sp[16];      // softplus' of my 32 columns as unorm16 pairs
-#pragma unroll
-        for (int hb = 0; hb < 2; ++hb) {           // two 16-column blocks
-          const int cb = c0 + hb * 16;
-          uint32_t a[16], b[16];
-          tc::tmem_ld16(tl + T1_DA + cb, a);
-          if (l > 0) tc::tmem_ld16(tl + T1_DB + cb, b);
-          tc::tmem_wait_ld();
-          uint32_t hi[8], lo[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float z0 = __uint_as_float(a[2 * j]), z1 = __uint_as_float(a[2 * j + 1]);
-            if (l > 0) {
-              z0 += __uint_as_float(b[2 * j]);
-              z1 += __uint_as_float(b[2 * j + 1]);
-            }
-            float d0 = 0.f, d1 = 0.f;
-            float h0 = t1_softplus<GRAD>(z0, d0);
-            float h1 = t1_softplus<GRAD>(z1, d1);
-            const int n0 = cb + 2 * j;
-            if (to_skip && part == 3) {            // columns 101..127 of the skip layer's input are the PE
-              if (n0 >= 101) { h0 = get_k(ape, n0 - 101); d0 = 0.f; }
-              if (n0 + 1 >= 101) { h1 = get_k(ape, n0 + 1 - 101); d1 = 0.f; }
-            }
-            if (l == 5) {
-              head = fmaf(h0, sw6[n0], head);
-              head = fmaf(h1, sw6[n0 + 1], head);
-              if (GRAD) {                          // delta5 = w6[n] / scale * softplus'(z5)
-                h0 = sw6[n0] * net.inv_scale * d0;
-                h1 = sw6[n0 + 1] * net.inv_scale * d1;
-              }
-            } else if (GRAD) {
-              const uint32_t u0 = __float2uint_rn(d0 * 65535.0f), u1 = __float2uint_rn(d1 * 65535.0f);
-              sp[hb * 8 + j] = u0 | (u1 << 16);
-            }
-            tc::split2(h0, h1, hi[j], lo[j]);
-          }
-          if (l < 5 || GRAD) {
-            tc::tmem_st8(tl + T1_AHI + (cb >> 1), hi);
-            tc::tmem_st8(tl + T1_ALO + (cb >> 1), lo);
-          }
-        }
+        // layer-specialised epilogues: the generic hidden layer carries no special-case instructions
+        if (l == 0) t1_fwd_epilogue<GRAD, false, false, false>(ec, l, head);
+        else if (l == 5) t1_fwd_epilogue<GRAD, true, false, true>(ec, l, head);
+        else if (l + 1 == net.skip_layer && part == 3) t1_fwd_epilogue<GRAD, true, true, false>(ec, l, head);
+        else t1_fwd_epilogue<GRAD, true, false, false>(ec, l, head);
         if (l < 5 || GRAD) {
           tc::tmem_wait_st();
           tc::tc_fence_before();
           tc::mbar_arrive(&bars->a_ready);
           if (warp == 0) TRACE1(30 + l);
-        }
-        if (GRAD && l < 5) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            scratch[(size_t)(l * 4 + j) * T1_EPI_THREADS + te] = make_uint4(sp[4 * j], sp[4 * j + 1], sp[4 * j + 2], sp[4 * j + 3]);
         }
         if (l == 5) {
           s_part[part * 128 + r] = head;
@@ -314,40 +397,30 @@ k_sdf_tc1(const DevScene sc, const DevNet net, const PointSource src, const uint
 #pragma unroll
       for (int j = 0; j < 8; ++j) gf[j] = sw6[128 + part * 8 + j] * net.inv_scale;
       for (int l = 5; l >= 1; --l) {
-        // softplus'(z_{l-1}) of my columns (thread-private, written in the forward pass)
+        // u codes / signs of layer l-1 for my columns (thread-private, written in the forward pass)
         uint4 spv[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) spv[j] = scratch[(size_t)((l - 1) * 4 + j) * T1_EPI_THREADS + te];
+        const uint32_t sgn = sgn_scratch[(size_t)(l - 1) * T1_EPI_THREADS + te];
+        if (l == 4) {
+          // gather the NEXT tile's features now (its lines were prefetched into L2 during lin1): the load latency
+          // hides behind this layer's MMAs and the next tile's staging shrinks to the smem writes
+          have_next = false;
+          if (it + 1 < my_tiles) {
+            float nx, ny, nz;
+            load_point((tile + gridDim.x) * 128 + r, nx, ny, nz);
+#pragma unroll
+            for (int c = 0; c < 7; ++c) nf7[c] = 0.f;
+            if (part < sc.n_levels) sparse_level<0>(sc, part, nx, ny, nz, nullptr, nf7);
+            have_next = true;
+          }
+        }
         tc::mbar_wait(&bars->d_full, ph_d & 1);
         ph_d++;
         tc::tc_fence_after();
         if (warp == 0) TRACE1(16 + (5 - l));
-        const uint32_t* spw = reinterpret_cast<const uint32_t*>(spv);
-        const bool is_skip = (l == net.skip_layer);
-#pragma unroll
-        for (int hb = 0; hb < 2; ++hb) {
-          const int cb = c0 + hb * 16;
-          uint32_t a[16], b[16];
-          tc::tmem_ld16(tl + T1_DA + cb, a);
-          tc::tmem_ld16(tl + T1_DB + cb, b);
-          tc::tmem_wait_ld();
-          uint32_t hi[8], lo[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float g0 = __uint_as_float(a[2 * j]) + __uint_as_float(b[2 * j]);
-            const float g1 = __uint_as_float(a[2 * j + 1]) + __uint_as_float(b[2 * j + 1]);
-            const uint32_t w = spw[hb * 8 + j];
-            const float d0 = (float)(w & 0xffffu) * (1.0f / 65535.0f), d1 = (float)(w >> 16) * (1.0f / 65535.0f);
-            const int n0 = cb + 2 * j;
-            if (is_skip && part == 3) {            // input-gradient of the PE columns of the skip layer
-              if (n0 >= 101) s_gpe[(n0 - 101) * 128 + r] = g0;
-              if (n0 + 1 >= 101) s_gpe[(n0 + 1 - 101) * 128 + r] = g1;
-            }
-            tc::split2(g0 * d0, g1 * d1, hi[j], lo[j]);
-          }
-          tc::tmem_st8(tl + T1_AHI + (cb >> 1), hi);
-          tc::tmem_st8(tl + T1_ALO + (cb >> 1), lo);
-        }
+        if (l == net.skip_layer && part == 3) t1_bwd_epilogue<true>(ec, spv, sgn);
+        else t1_bwd_epilogue<false>(ec, spv, sgn);
         {   // feature-gradient columns 128 + part*8 ..
           uint32_t a[8], b[8];
           asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -369,11 +442,20 @@ k_sdf_tc1(const DevScene sc, const DevNet net, const PointSource src, const uint
 #pragma unroll
       for (int j = 0; j < 8; ++j)
         if (part * 8 + j < 28) s_gf[(part * 8 + j) * 128 + r] = gf[j];
+      epi_bar();                                   // s_gpe (skip part) and s_gf complete
+      // d feats / d x for level `part` (re-gather; lines were touched a tile ago, L2 hits) — issued before
+      // waiting for the lin0 reverse MMAs so its latency overlaps them
+      float o3[3] = {0.f, 0.f, 0.f};
+      if (part < sc.n_levels) {
+        float g7[7];
+#pragma unroll
+        for (int c = 0; c < 7; ++c) g7[c] = s_gf[(part * 7 + c) * 128 + r];
+        sparse_level<1>(sc, part, px, py, pz, g7, o3);
+      }
       // ---- reverse of lin0: g_pe += delta0 . W0 (N = 32) ----
       tc::mbar_wait(&bars->d_full, ph_d & 1);
       ph_d++;
       tc::tc_fence_after();
-      epi_bar();                                   // s_gpe (skip part) and s_gf complete
       if (part == 0) {
         uint32_t a[16], b[16];
 #pragma unroll
@@ -389,14 +471,6 @@ k_sdf_tc1(const DevScene sc, const DevNet net, const PointSource src, const uint
         }
       }
       tc::tc_fence_before();
-      // d feats / d x for level `part` (re-gather; the data was touched ~50 us ago, L2 hits)
-      float o3[3] = {0.f, 0.f, 0.f};
-      if (part < sc.n_levels) {
-        float g7[7];
-#pragma unroll
-        for (int c = 0; c < 7; ++c) g7[c] = s_gf[(part * 7 + c) * 128 + r];
-        sparse_level<1>(sc, part, px, py, pz, g7, o3);
-      }
       epi_bar();                                   // all s_gf reads done, s_gpe final
       float* s_pg = s_gf;                          // reuse as [4][3][128]
       s_pg[(part * 3 + 0) * 128 + r] = o3[0];
@@ -451,14 +525,20 @@ k_sdf_tc1(const DevScene sc, const DevNet net, const PointSource src, const uint
             if (p < 6) {
               // forward chunk: N = 128, K = 32 ; hi at +0, lo at +8192 B ; K step = 2 groups = 4096 B
               const uint32_t w0 = (uint32_t)d128 | wa, dh = (uint32_t)(d128 >> 32);
-              if (p == 0 || c == 4) {
-                const uint32_t a0 = (p == 0) ? ape_lo : afeat_lo;
+              if (p == 0) {
+                const uint32_t a0 = ape_lo;
                 if (first) tc::mma_ss_w<false>(tD, a0, dh, w0, dh, id128); else tc::mma_ss_w<true>(tD, a0, dh, w0, dh, id128);
                 tc::mma_ss_w<true>(tD, a0 + 512, dh, w0, dh, id128);
                 tc::mma_ss_w<true>(tD, a0, dh, w0 + 512, dh, id128);
                 tc::mma_ss_w<true>(tD, a0 + 256, dh, w0 + 256, dh, id128);
                 tc::mma_ss_w<true>(tD, a0 + 768, dh, w0 + 256, dh, id128);
                 tc::mma_ss_w<true>(tD, a0 + 256, dh, w0 + 768, dh, id128);
+              } else if (c >= 4) {
+                // half chunk (K = 16): feature columns; chunk 4 -> K step 0, chunk 5 -> K step 1 of the smem A operand
+                const uint32_t a0 = afeat_lo + (c - 4) * 256;
+                tc::mma_ss_w<true>(tD, a0, dh, w0, dh, id128);
+                tc::mma_ss_w<true>(tD, a0 + 512, dh, w0, dh, id128);
+                tc::mma_ss_w<true>(tD, a0, dh, w0 + 256, dh, id128);
               } else {
                 const uint32_t ah = tAhi + c * 16, al = tAlo + c * 16;
                 if (first) tc::mma_ts_w<false>(tD, ah, w0, dh, id128); else tc::mma_ts_w<true>(tD, ah, w0, dh, id128);
@@ -565,13 +645,15 @@ int surf_build_tc1_weights(const std::vector<std::vector<float>>& W, const surf_
   }
   for (int l = 1; l < 6; ++l) {
     const int O = in->out_dim[l], I = in->in_dim[l];
-    for (int c = 0; c < 5; ++c) {
-      const size_t b = add_chunk(128, 32);
+    for (int c = 0; c < 6; ++c) {
+      const int K = c < 4 ? 32 : 16;                  // 4 hidden chunks, then the feature / bias columns in two halves
+      const int kbase = c < 4 ? c * 32 : 128 + (c - 4) * 16;
+      const size_t b = add_chunk(128, K);
       for (int n = 0; n < O && n < 128; ++n)
-        for (int kk = 0; kk < 32; ++kk) {
-          const int k = c * 32 + kk;
-          if (k < I) put(b, 128, 32, n, kk, W[l][(size_t)n * I + k]);
-          else if (k == 156) put(b, 128, 32, n, kk, in->h_bias[l][n]);
+        for (int kk = 0; kk < K; ++kk) {
+          const int k = kbase + kk;
+          if (k < I) put(b, 128, K, n, kk, W[l][(size_t)n * I + k]);
+          else if (k == 156) put(b, 128, K, n, kk, in->h_bias[l][n]);
         }
       nc++;
     }
@@ -611,7 +693,7 @@ int surf_build_tc1_weights(const std::vector<std::vector<float>>& W, const surf_
   SURF_CUDA(cudaStreamSynchronize(st));
   net->tc1_blob = (const uint8_t*)p;
   // softplus' scratch: 5 layers x 4 x 512 threads x 16 B per CTA
-  rc = dev_alloc(net, &p, (size_t)net->n_sm * 5 * 4 * T1_EPI_THREADS * sizeof(uint4));
+  rc = dev_alloc(net, &p, (size_t)net->n_sm * (5 * 4 * T1_EPI_THREADS + 5 * T1_EPI_THREADS / 4) * sizeof(uint4));
   if (rc) return rc;
   net->tc1_scratch = p;
   return 0;

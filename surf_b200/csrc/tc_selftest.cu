@@ -96,10 +96,13 @@ __global__ void __launch_bounds__(128, 1) k_tc_bench(int N, int reps, int mode, 
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint32_t s_tmem;
   __shared__ __align__(8) uint64_t s_bar;
+  __shared__ __align__(8) uint64_t s_bar2[4];
   const int tid = threadIdx.x, warp = tid >> 5;
   if (warp == 0) tc::tmem_alloc<512>(&s_tmem);
   if (tid == 0) {
-    tc::mbar_init(&s_bar, mode >= 4 ? mode - 3 : 1);
+    for (int i = 0; i < 4; ++i) tc::mbar_init(&s_bar2[i], i == 2 ? 1 : 1000000);
+    tc::mbar_arrive(&s_bar2[2]);          // barrier 2 completes its phase 0 immediately
+    tc::mbar_init(&s_bar, mode >= 10 ? 2 : (mode >= 4 ? mode - 3 : 1));
     tc::mbar_fence_init();
   }
   for (int i = tid; i < 16384; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0;
@@ -109,7 +112,7 @@ __global__ void __launch_bounds__(128, 1) k_tc_bench(int N, int reps, int mode, 
   tc::tc_fence_after();
   const uint32_t tbase = s_tmem;
   // mode >= 4: (mode - 3) issuer threads (lane 0 of warps 0..), each with its own accumulator (N <= 128), TS form
-  const int n_issuers = mode >= 4 ? mode - 3 : 1;
+  const int n_issuers = mode >= 10 ? 2 : (mode >= 4 ? mode - 3 : 1);
   if ((tid & 31) == 0 && warp < n_issuers) {
     const uint32_t idesc = tc::idesc_f16(128, N, 0);
     const uint64_t d0 = tc::smem_desc_kmajor(tc::smem_u32(smem), (uint32_t)N * 16, 128);
@@ -117,6 +120,18 @@ __global__ void __launch_bounds__(128, 1) k_tc_bench(int N, int reps, int mode, 
     const uint64_t a0 = tc::smem_desc_kmajor(tc::smem_u32(smem) + 32768, 2048, 128);
     const uint32_t alo = (uint32_t)a0, ahi = (uint32_t)(a0 >> 32);
     const long long t0 = clock64();
+    if (mode >= 10) {
+      // mode 10: 2 issuers, commit to a scratch barrier after every 6 MMAs
+      // mode 11: additionally wait on an (already completed) barrier before every group of 6
+      // mode 12: mode 10 with distinct A/B addresses per MMA (like the real loop)
+      for (int r = 0; r < reps; ++r) {
+        const uint32_t tD = tbase + warp * 128;
+        if (mode == 11 && (r % 6) == 0) tc::mbar_wait(&s_bar2[2], 0);
+        const uint32_t off = (mode == 12) ? (uint32_t)(r % 6) * 64u : 0u;
+        tc::mma_ts_w<true>(tD, tbase + 448 + (r & 1) * 8, dlo + off, dhi, idesc);
+        if ((r % 6) == 5) tc::mma_commit(&s_bar2[warp]);
+      }
+    } else
     for (int r = 0; r < reps; ++r) {
       uint32_t tD = tbase + (((mode & 1) && mode < 4 && (r & 1)) ? 256 : 0);
       if (mode >= 4) tD = tbase + warp * 128;

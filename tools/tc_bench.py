@@ -11,7 +11,10 @@ for N in (64, 128):
     for mode in (4, 5, 6):
         lib.surf_tc_bench(N, 64, mode, out)
         print("N=%3d TS %d issuer threads x 64 mma: done %6d clk -> %.1f clk per mma aggregate" % (N, mode - 3, out[1], out[1] / (64 * (mode - 3))))
-for N in (256,):
+for mode, name in ((5, "2 issuers plain"), (10, "2 issuers + commit/6"), (11, "2 issuers + wait + commit/6"), (12, "2 issuers + commit/6 + distinct addr")):
+    lib.surf_tc_bench(128, 60, mode, out)
+    print("N=128 %-40s 60 mma each: %.1f clk per mma per thread" % (name, out[1] / 60))
+for N in ():
     for mode, name in ((0, "TS 1acc"), (1, "TS 2acc"), (2, "SS 1acc"), (3, "SS 2acc")):
         if N == 256 and mode in (1, 3):
             continue
