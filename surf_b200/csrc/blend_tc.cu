@@ -94,7 +94,7 @@ __device__ __forceinline__ void aop_put(uint8_t* aop, int r, int k, float v) {
 
 // one layer on the tensor core: D[128 x N] = A_op[128 x K] * W^T, issued by one thread
 template <int N, int KSTEPS>
-__device__ __forceinline__ void bt_issue(uint32_t tD, uint32_t aop_addr, uint32_t w_addr, uint64_t* bar) {
+__device__ __forceinline__ void bt_issue(uint32_t tD, uint32_t aop_addr, uint32_t w_addr, uint64_t* bar, bool fast) {
   const uint32_t idesc = tc::idesc_f16(128, N, 0);
   const uint64_t da = tc::smem_desc_kmajor(0, 2048, 128), db = tc::smem_desc_kmajor(0, N * 16, 128);
   const uint32_t ah = (uint32_t)(da >> 32), bh = (uint32_t)(db >> 32);
@@ -105,8 +105,8 @@ __device__ __forceinline__ void bt_issue(uint32_t tD, uint32_t aop_addr, uint32_
   for (int ks = 0; ks < KSTEPS; ++ks) {
     if (ks == 0) tc::mma_ss_w<false>(tD, a0, ah, b0, bh, idesc);
     else tc::mma_ss_w<true>(tD, a0 + ks * A_KS, ah, b0 + ks * B_KS, bh, idesc);
-    tc::mma_ss_w<true>(tD, a0 + A_LO + ks * A_KS, ah, b0 + ks * B_KS, bh, idesc);
-    tc::mma_ss_w<true>(tD, a0 + ks * A_KS, ah, b0 + B_LO + ks * B_KS, bh, idesc);
+    if (!fast) tc::mma_ss_w<true>(tD, a0 + A_LO + ks * A_KS, ah, b0 + ks * B_KS, bh, idesc);
+    if (!fast) tc::mma_ss_w<true>(tD, a0 + ks * A_KS, ah, b0 + B_LO + ks * B_KS, bh, idesc);
   }
   tc::mma_commit(bar);
 }
@@ -115,7 +115,8 @@ __global__ void __launch_bounds__(BT_THREADS, 2)
 k_blend_tc(const uint8_t* __restrict__ wtc, const float* __restrict__ wf32, float s_abs, const float* __restrict__ feat,
            const float* __restrict__ rdiff, const uint8_t* __restrict__ mask, int V, int packed19,
            const int32_t* __restrict__ list, const int32_t* __restrict__ count, int64_t n, float* __restrict__ rgb_out,
-           uint8_t* __restrict__ views_out) {
+           uint8_t* __restrict__ views_out, int fast_i) {
+  const bool fast = fast_i != 0;
   extern __shared__ __align__(1024) uint8_t smem[];
   BtBars* bars = reinterpret_cast<BtBars*>(smem + SB_BAR);
   const float* WF = reinterpret_cast<const float*>(smem + SB_WF);
@@ -261,7 +262,7 @@ k_blend_tc(const uint8_t* __restrict__ wtc, const float* __restrict__ wf32, floa
     }
     publish();
     // ---- base_fc.0 : 57(64) -> 64, ELU ----
-    if (tid == 0) bt_issue<64, 4>(tbase, aop_a, w_a + W_BASE0, &bars->mma_done);
+    if (tid == 0) bt_issue<64, 4>(tbase, aop_a, w_a + W_BASE0, &bars->mma_done, fast);
     wait_mma();
     {
       uint32_t acc[32];
@@ -277,7 +278,7 @@ k_blend_tc(const uint8_t* __restrict__ wtc, const float* __restrict__ wf32, floa
     }
     publish();
     // ---- base_fc.2 : 64 -> 32, ELU -> x (fp32) ; next A operand = x * pooling weight ----
-    if (tid == 0) bt_issue<32, 4>(tbase, aop_a, w_a + W_BASE1, &bars->mma_done);
+    if (tid == 0) bt_issue<32, 4>(tbase, aop_a, w_a + W_BASE1, &bars->mma_done, fast);
     wait_mma();
     {
       uint32_t acc[16];
@@ -295,7 +296,7 @@ k_blend_tc(const uint8_t* __restrict__ wtc, const float* __restrict__ wf32, floa
     }
     publish();
     // ---- vis_fc.0 : 32 -> 32, ELU ----
-    if (tid == 0) bt_issue<32, 2>(tbase, aop_a, w_a + W_VIS0, &bars->mma_done);
+    if (tid == 0) bt_issue<32, 2>(tbase, aop_a, w_a + W_VIS0, &bars->mma_done, fast);
     wait_mma();
     {
       uint32_t acc[16];
@@ -308,7 +309,7 @@ k_blend_tc(const uint8_t* __restrict__ wtc, const float* __restrict__ wf32, floa
     }
     publish();
     // ---- vis_fc.2 : 32 -> 33, ELU ; x += x_res ; vis = sigmoid(.) * mask ----
-    if (tid == 0) bt_issue<48, 2>(tbase, aop_a, w_a + W_VIS1, &bars->mma_done);
+    if (tid == 0) bt_issue<48, 2>(tbase, aop_a, w_a + W_VIS1, &bars->mma_done, fast);
     wait_mma();
     {
       uint32_t acc[16];
@@ -336,7 +337,7 @@ k_blend_tc(const uint8_t* __restrict__ wtc, const float* __restrict__ wf32, floa
     }
     publish();
     // ---- vis_fc2.0 : 32 -> 32, ELU ; vis_fc2.2 : 32 -> 1 (CUDA cores), sigmoid * mask ----
-    if (tid == 0) bt_issue<32, 2>(tbase, aop_a, w_a + W_V20, &bars->mma_done);
+    if (tid == 0) bt_issue<32, 2>(tbase, aop_a, w_a + W_V20, &bars->mma_done, fast);
     wait_mma();
     {
       uint32_t acc[16];
@@ -367,7 +368,7 @@ k_blend_tc(const uint8_t* __restrict__ wtc, const float* __restrict__ wf32, floa
     }
     publish();
     // ---- rgb_fc.0 : 37(48) -> 16, ELU ; rgb_fc.2/.4 : 16 -> 8 -> 1 on the CUDA cores ----
-    if (tid == 0) bt_issue<16, 3>(tbase, aop_a, w_a + W_RGB0, &bars->mma_done);
+    if (tid == 0) bt_issue<16, 3>(tbase, aop_a, w_a + W_RGB0, &bars->mma_done, fast);
     wait_mma();
     {
       float* A16 = F;                                   // [16][BS], feat buffer is free now
@@ -512,7 +513,8 @@ int launch_blend_tc(const surf_net* n, const float* d_feat, const float* d_raydi
   const int grid = (int)(tiles < cap ? tiles : cap);
   surf_time_begin(3, st);
   k_blend_tc<<<grid, BT_THREADS, SB_TOTAL, st>>>(n->blend_tc_w, n->blend_tc_f, n->dev.blend_s, d_feat, d_raydiff, d_mask, V,
-                                                 packed19 ? 1 : 0, list, count, n_pts, d_rgb, d_views);
+                                                 packed19 ? 1 : 0, list, count, n_pts, d_rgb, d_views,
+                                                 surf_mlp_mode() == 4 ? 1 : 0);
   surf_time_end(3, st);
   SURF_LAUNCH_CHECK();
   return 0;

@@ -445,7 +445,7 @@ int surf_build_tc1_weights(const std::vector<std::vector<float>>& W, const surf_
 static int g_mlp_mode = 0;
 int surf_mlp_mode() { return g_mlp_mode; }
 extern "C" int surf_set_mlp_mode(int32_t mode) {
-  SURF_CHECK_ARG(mode >= 0 && mode <= 3, "mlp mode must be 0..3");
+  SURF_CHECK_ARG(mode >= 0 && mode <= 4, "mlp mode must be 0..4");
   g_mlp_mode = mode;
   return 0;
 }

@@ -281,6 +281,8 @@ k_sdf_tc_fwd(const DevScene sc, const DevNet net, const PointSource src, const u
     // the accumulate=false MMA; issuer B (sub 1) takes chunks 1,3 and starts once that first MMA has completed.
     const int g = (warp - TC_EPI_WARPS) >> 1;
     const int sub = (warp - TC_EPI_WARPS) & 1;
+    const bool fast = (two_issuers & 2) != 0;   // single fp16 MMA per product (opt-in reduced-precision mode)
+    two_issuers &= 1;
     if (lane == 0) {
       const uint32_t idesc = tc::idesc_f16(128, 128, 0);
       const uint32_t ring = tc::smem_u32(smem + TS_RING);
@@ -326,11 +328,11 @@ k_sdf_tc_fwd(const DevScene sc, const DevNet net, const PointSource src, const u
               } else {
                 tc::mma_ss_w<true>(tD, a0, desc_hi, w0, desc_hi, idesc);
               }
-              tc::mma_ss_w<true>(tD, a0 + 512, desc_hi, w0, desc_hi, idesc);
-              tc::mma_ss_w<true>(tD, a0, desc_hi, w0 + 512, desc_hi, idesc);
+              if (!fast) tc::mma_ss_w<true>(tD, a0 + 512, desc_hi, w0, desc_hi, idesc);
+              if (!fast) tc::mma_ss_w<true>(tD, a0, desc_hi, w0 + 512, desc_hi, idesc);
               tc::mma_ss_w<true>(tD, a0 + 256, desc_hi, w0 + 256, desc_hi, idesc);
-              tc::mma_ss_w<true>(tD, a0 + 768, desc_hi, w0 + 256, desc_hi, idesc);
-              tc::mma_ss_w<true>(tD, a0 + 256, desc_hi, w0 + 768, desc_hi, idesc);
+              if (!fast) tc::mma_ss_w<true>(tD, a0 + 768, desc_hi, w0 + 256, desc_hi, idesc);
+              if (!fast) tc::mma_ss_w<true>(tD, a0 + 256, desc_hi, w0 + 768, desc_hi, idesc);
             } else {
               const uint32_t ah = tAhi + c * 16, al = tAlo + c * 16;
               if (c == 0) {
@@ -339,11 +341,11 @@ k_sdf_tc_fwd(const DevScene sc, const DevNet net, const PointSource src, const u
               } else {
                 tc::mma_ts_w<true>(tD, ah, w0, desc_hi, idesc);
               }
-              tc::mma_ts_w<true>(tD, al, w0, desc_hi, idesc);
-              tc::mma_ts_w<true>(tD, ah, w0 + 512, desc_hi, idesc);
+              if (!fast) tc::mma_ts_w<true>(tD, al, w0, desc_hi, idesc);
+              if (!fast) tc::mma_ts_w<true>(tD, ah, w0 + 512, desc_hi, idesc);
               tc::mma_ts_w<true>(tD, ah + 8, w0 + 256, desc_hi, idesc);
-              tc::mma_ts_w<true>(tD, al + 8, w0 + 256, desc_hi, idesc);
-              tc::mma_ts_w<true>(tD, ah + 8, w0 + 768, desc_hi, idesc);
+              if (!fast) tc::mma_ts_w<true>(tD, al + 8, w0 + 256, desc_hi, idesc);
+              if (!fast) tc::mma_ts_w<true>(tD, ah + 8, w0 + 768, desc_hi, idesc);
             }
             tc::mma_commit(&bars->w_empty[slot]);
           }
@@ -442,7 +444,7 @@ int launch_sdf_tc_fwd(const surf_scene* s, const surf_net* n, const PointSource&
   const int grid = (int)(pairs < n->n_sm ? pairs : n->n_sm);
   surf_time_begin(1, st);
   k_sdf_tc_fwd<<<grid, TC_THREADS, TS_TOTAL, st>>>(s->dev, n->dev, src, n->tc_blob, d_sdf, negate ? 1 : 0,
-                                                   surf_mlp_mode() == 2 ? 1 : 0);
+                                                   (surf_mlp_mode() == 2 ? 1 : 0) | (surf_mlp_mode() == 4 ? 2 : 0));
   surf_time_end(1, st);
   SURF_LAUNCH_CHECK();
   return 0;

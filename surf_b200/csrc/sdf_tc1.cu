@@ -383,7 +383,7 @@ k_sdf_tc1(const DevScene sc, const DevNet net, const PointSource src, const uint
 #pragma unroll
             for (int c = 0; c < 28; ++c) s = fmaf(get_k(afeat, c), sw6[128 + c], s);
             s *= net.inv_scale;
-            if (id >= 0) sdf_out[id] = negate ? -s : s;
+            if (id >= 0) sdf_out[id] = (negate & 1) ? -s : s;
           }
           if (!GRAD) {
             tc::tc_fence_before();
@@ -497,6 +497,7 @@ k_sdf_tc1(const DevScene sc, const DevNet net, const PointSource src, const uint
   } else if (warp < T1_EPI_WARPS + 2) {
     // =============================== MMA issuers: sub 0 -> D_a, sub 1 -> D_b ===============================
     const int sub = warp - T1_EPI_WARPS;
+    const bool fast = (negate & 2) != 0;      // single fp16 MMA per product (opt-in reduced-precision mode)
     if (lane == 0) {
       const uint32_t ring = tc::smem_u32(smem + S1_RING);
       const uint32_t tD = tbase + (sub ? T1_DB : T1_DA);
@@ -528,36 +529,36 @@ k_sdf_tc1(const DevScene sc, const DevNet net, const PointSource src, const uint
               if (p == 0) {
                 const uint32_t a0 = ape_lo;
                 if (first) tc::mma_ss_w<false>(tD, a0, dh, w0, dh, id128); else tc::mma_ss_w<true>(tD, a0, dh, w0, dh, id128);
-                tc::mma_ss_w<true>(tD, a0 + 512, dh, w0, dh, id128);
-                tc::mma_ss_w<true>(tD, a0, dh, w0 + 512, dh, id128);
+                if (!fast) tc::mma_ss_w<true>(tD, a0 + 512, dh, w0, dh, id128);
+                if (!fast) tc::mma_ss_w<true>(tD, a0, dh, w0 + 512, dh, id128);
                 tc::mma_ss_w<true>(tD, a0 + 256, dh, w0 + 256, dh, id128);
-                tc::mma_ss_w<true>(tD, a0 + 768, dh, w0 + 256, dh, id128);
-                tc::mma_ss_w<true>(tD, a0 + 256, dh, w0 + 768, dh, id128);
+                if (!fast) tc::mma_ss_w<true>(tD, a0 + 768, dh, w0 + 256, dh, id128);
+                if (!fast) tc::mma_ss_w<true>(tD, a0 + 256, dh, w0 + 768, dh, id128);
               } else if (c >= 4) {
                 // half chunk (K = 16): feature columns; chunk 4 -> K step 0, chunk 5 -> K step 1 of the smem A operand
                 const uint32_t a0 = afeat_lo + (c - 4) * 256;
                 tc::mma_ss_w<true>(tD, a0, dh, w0, dh, id128);
-                tc::mma_ss_w<true>(tD, a0 + 512, dh, w0, dh, id128);
-                tc::mma_ss_w<true>(tD, a0, dh, w0 + 256, dh, id128);
+                if (!fast) tc::mma_ss_w<true>(tD, a0 + 512, dh, w0, dh, id128);
+                if (!fast) tc::mma_ss_w<true>(tD, a0, dh, w0 + 256, dh, id128);
               } else {
                 const uint32_t ah = tAhi + c * 16, al = tAlo + c * 16;
                 if (first) tc::mma_ts_w<false>(tD, ah, w0, dh, id128); else tc::mma_ts_w<true>(tD, ah, w0, dh, id128);
-                tc::mma_ts_w<true>(tD, al, w0, dh, id128);
-                tc::mma_ts_w<true>(tD, ah, w0 + 512, dh, id128);
+                if (!fast) tc::mma_ts_w<true>(tD, al, w0, dh, id128);
+                if (!fast) tc::mma_ts_w<true>(tD, ah, w0 + 512, dh, id128);
                 tc::mma_ts_w<true>(tD, ah + 8, w0 + 256, dh, id128);
-                tc::mma_ts_w<true>(tD, al + 8, w0 + 256, dh, id128);
-                tc::mma_ts_w<true>(tD, ah + 8, w0 + 768, dh, id128);
+                if (!fast) tc::mma_ts_w<true>(tD, al + 8, w0 + 256, dh, id128);
+                if (!fast) tc::mma_ts_w<true>(tD, ah + 8, w0 + 768, dh, id128);
               }
             } else if (p < 11) {
               // reverse chunk: N = 160, K = 32 ; hi at +0, lo at +10240 B ; K step = 2 groups = 5120 B
               const uint32_t w0 = (uint32_t)d160 | wa, dh = (uint32_t)(d160 >> 32);
               const uint32_t ah = tAhi + c * 16, al = tAlo + c * 16;
               if (first) tc::mma_ts_w<false>(tD, ah, w0, dh, id160); else tc::mma_ts_w<true>(tD, ah, w0, dh, id160);
-              tc::mma_ts_w<true>(tD, al, w0, dh, id160);
-              tc::mma_ts_w<true>(tD, ah, w0 + 640, dh, id160);
+              if (!fast) tc::mma_ts_w<true>(tD, al, w0, dh, id160);
+              if (!fast) tc::mma_ts_w<true>(tD, ah, w0 + 640, dh, id160);
               tc::mma_ts_w<true>(tD, ah + 8, w0 + 320, dh, id160);
-              tc::mma_ts_w<true>(tD, al + 8, w0 + 320, dh, id160);
-              tc::mma_ts_w<true>(tD, ah + 8, w0 + 960, dh, id160);
+              if (!fast) tc::mma_ts_w<true>(tD, al + 8, w0 + 320, dh, id160);
+              if (!fast) tc::mma_ts_w<true>(tD, ah + 8, w0 + 960, dh, id160);
             } else {
               // reverse of lin0: N = 32, K = 64 per chunk (4 K steps) ; hi at +0, lo at +4096 B ; K step = 1024 B
               const uint32_t w0 = (uint32_t)d32 | wa, dh = (uint32_t)(d32 >> 32);
@@ -565,8 +566,8 @@ k_sdf_tc1(const DevScene sc, const DevNet net, const PointSource src, const uint
               for (int ks = 0; ks < 4; ++ks) {
                 const uint32_t ah = tAhi + c * 32 + ks * 8, al = tAlo + c * 32 + ks * 8;
                 if (first && ks == 0) tc::mma_ts_w<false>(tD, ah, w0, dh, id32); else tc::mma_ts_w<true>(tD, ah, w0 + ks * 64, dh, id32);
-                tc::mma_ts_w<true>(tD, al, w0 + ks * 64, dh, id32);
-                tc::mma_ts_w<true>(tD, ah, w0 + 256 + ks * 64, dh, id32);
+                if (!fast) tc::mma_ts_w<true>(tD, al, w0 + ks * 64, dh, id32);
+                if (!fast) tc::mma_ts_w<true>(tD, ah, w0 + 256 + ks * 64, dh, id32);
               }
             }
             tc::mma_commit(&bars->w_empty[slot]);
@@ -713,10 +714,10 @@ int launch_sdf_tc1(const surf_scene* s, const surf_net* n, const PointSource& sr
   surf_time_begin(d_grad ? 0 : 1, st);
   if (d_grad) {
     k_sdf_tc1<true><<<grid, T1_THREADS, S1_TOTAL, st>>>(s->dev, n->dev, src, n->tc1_blob, g_t1_stream, d_sdf, d_grad,
-                                                        (uint4*)n->tc1_scratch, negate ? 1 : 0);
+                                                        (uint4*)n->tc1_scratch, (negate ? 1 : 0) | (surf_mlp_mode() == 4 ? 2 : 0));
   } else {
     k_sdf_tc1<false><<<grid, T1_THREADS, S1_TOTAL, st>>>(s->dev, n->dev, src, n->tc1_blob, g_t1_stream, d_sdf, nullptr,
-                                                         (uint4*)n->tc1_scratch, negate ? 1 : 0);
+                                                         (uint4*)n->tc1_scratch, (negate ? 1 : 0) | (surf_mlp_mode() == 4 ? 2 : 0));
   }
   surf_time_end(d_grad ? 0 : 1, st);
   SURF_LAUNCH_CHECK();

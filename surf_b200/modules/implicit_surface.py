@@ -371,16 +371,20 @@ class ImplicitSurface(nn.Module):
         n = rays_o.shape[0]
         if near.shape[0] == 1 and n != 1:
             near, far = near.expand(n, 1), far.expand(n, 1)
-        if self.perturb > 0 and t_rand is None:
-            t_rand = self.draw_chunk_randoms(n, chunk)
+        draw = self.perturb > 0 and t_rand is None
         if t_rand is not None:
             t_rand = t_rand.to(rays_o.device, non_blocking=True)
         step_rays = max(chunk, (self.ray_batch // chunk) * chunk)
         acc = {k: [] for k in ("color_fine", "val_normal", "sdf_depth", "render_depth")}
         for r0 in range(0, n, step_rays):
             r1 = min(n, r0 + step_rays)
+            tr = None if t_rand is None else t_rand[r0:r1]
+            if draw:
+                # the reference's jitter stream is drawn on the host, batch by batch: launches are asynchronous, so
+                # the draw for this batch overlaps the kernels of the previous one (same stream order: chunks ascend)
+                tr = self.draw_chunk_randoms(r1 - r0, chunk).pin_memory().to(rays_o.device, non_blocking=True)
             t = self._render_device(scene, rays_o[r0:r1], rays_d[r0:r1], near[r0:r1], far[r0:r1],
-                                    None if t_rand is None else t_rand[r0:r1], None, cos_anneal_ratio, chunk, lean=True)
+                                    tr, None, cos_anneal_ratio, chunk, lean=True)
             for k in acc:
                 acc[k].append(t[k])
         return {k: (v[0] if len(v) == 1 else torch.cat(v, dim=0)) for k, v in acc.items()}

@@ -166,3 +166,29 @@ def test_tc_blend_vs_reference(name, tc_mode):
                  "tc blend rgb, nothing visible")
     again = m.color_network(fv.cuda(), rd.cuda(), mk.cuda()).cpu()
     assert torch.equal(got, again)
+
+
+# ------------------------------------------------------------------------------------------------
+# opt-in reduced-precision mode (north_star: "1e-2 relative for the opt-in bf16 MLP mode"): mode 4 issues one
+# fp16 MMA per product instead of three (fp16 rather than bf16: same cost, ~8x smaller error)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["render_v2_perturbed", "render_v2_init"])
+def test_fast_mode_within_1e2(name):
+    import surf_oracle as O
+    from helpers import RTOL_BF16
+    _lib.set_mlp_mode(4)
+    try:
+        g, sc, d, m, ps = _setup(name)
+        pv = torch.from_numpy(g["out"]["_pts_valid"]).cuda()
+        sdf, grad = m.sdf_network.gradient(pv, ps, with_sdf=True)
+        assert_close(sdf, g["out"]["_sdf_full"][:, :1], RTOL_BF16, "fast-mode sdf")
+        assert_close(grad, g["out"]["_grad_valid"], RTOL_BF16, "fast-mode gradient")
+        assert_close(m.sdf_network.sdf(pv, ps), g["out"]["_sdf_full"][:, :1], RTOL_BF16, "fast-mode sdf (forward kernel)")
+        o = g["out"]
+        fv, rd, mk = (torch.from_numpy(o[k]) for k in ("_feat_views", "_ray_diff", "_view_mask"))
+        rgb = m.color_network(fv.cuda(), rd.cuda(), mk.cuda())
+        assert_close(rgb, o["_blend_rgb"], RTOL_BF16, "fast-mode blend rgb")
+        err = float((sdf.cpu() - torch.from_numpy(o["_sdf_full"][:, :1])).abs().max())
+        assert err > 1e-6, "fast mode should differ measurably from the fp32-grade path"
+    finally:
+        _lib.set_mlp_mode(0)
