@@ -296,7 +296,8 @@ k_sdf_tc_fwd(const DevScene sc, const DevNet net, const PointSource src, const u
       const uint32_t afeat_lo = (uint32_t)d0 | (afeat >> 4);
       const uint32_t ape_lo = (uint32_t)d0 | (ape >> 4);
       uint32_t ph_a = 0;
-      int64_t s = 0;     // chunk stream position
+      int slot = 0;            // ring position / parity kept incrementally (a 64-bit % per chunk costs ~400 clk)
+      uint32_t ring_par = 0;
       // The two tile pipelines have identical timing, so they would run in lockstep (both in their MMA phase,
       // then both in their epilogue phase).  Offset them once: Y's issuer starts after X has issued layer 1,
       // from then on X's epilogues overlap Y's MMAs and vice versa.
@@ -314,11 +315,10 @@ k_sdf_tc_fwd(const DevScene sc, const DevNet net, const PointSource src, const u
             ph_f++;
             tc::tc_fence_after();
           }
-          for (int c = 0; c < nch; ++c, ++s) {
+          for (int c = 0; c < nch; ++c, slot = (slot + 1 == TC_NSLOT) ? 0 : slot + 1, ring_par ^= (slot == 0)) {
             // one issuer (deterministic accumulation order) or chunks alternating between the two issuers
             if (two_issuers ? ((c & 1) != sub) : (sub != 0)) continue;
-            const int slot = (int)(s % TC_NSLOT);
-            tc::mbar_wait(&bars->w_full[slot], (uint32_t)((s / TC_NSLOT) & 1));
+            tc::mbar_wait(&bars->w_full[slot], ring_par);
             // descriptor low words (address field is in 16-byte units): slot base, +256 per K step, +512 for lo
             const uint32_t w0 = ring_lo + slot * (TC_CHUNK_BYTES >> 4);
             if (l == 0 || c == 4) {
@@ -360,11 +360,13 @@ k_sdf_tc_fwd(const DevScene sc, const DevNet net, const PointSource src, const u
     if (lane == 0) {
       const int64_t total = my_pairs * TC_CHUNKS_FWD;
       uint8_t* ring = smem + TS_RING;
-      for (int64_t s = 0; s < total; ++s) {
-        const int slot = (int)(s % TC_NSLOT);
-        if (s >= TC_NSLOT) tc::mbar_wait(&bars->w_empty[slot], (uint32_t)(((s / TC_NSLOT) - 1) & 1));
+      int slot = 0, cid = 0;
+      uint32_t par = 1;
+      for (int64_t s = 0; s < total; ++s, slot = (slot + 1 == TC_NSLOT) ? 0 : slot + 1, par ^= (slot == 0),
+                   cid = (cid + 1 == TC_CHUNKS_FWD) ? 0 : cid + 1) {
+        if (s >= TC_NSLOT) tc::mbar_wait(&bars->w_empty[slot], par);
         tc::mbar_arrive_expect_tx(&bars->w_full[slot], TC_CHUNK_BYTES);
-        tc::bulk_g2s(ring + slot * TC_CHUNK_BYTES, wblob + (size_t)(s % TC_CHUNKS_FWD) * TC_CHUNK_BYTES,
+        tc::bulk_g2s(ring + slot * TC_CHUNK_BYTES, wblob + (size_t)cid * TC_CHUNK_BYTES,
                      TC_CHUNK_BYTES, &bars->w_full[slot]);
       }
     }

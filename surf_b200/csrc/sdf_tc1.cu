@@ -22,7 +22,6 @@
 #define T1_THREADS ((T1_EPI_WARPS + 3) * 32)     // + 2 MMA issuers + 1 weight loader
 #define T1_SLOT_BYTES 20480                      // N = 160 x K = 32 x (hi + lo)
 #define T1_NSLOT 7
-#define T1_MAXCHUNK 64
 
 #define T1_DA 0u
 #define T1_DB 160u
@@ -41,24 +40,25 @@
 #define S1_TOTAL (S1_BAR + 256)
 
 #ifdef TC_TRACE
+// cheap in-kernel timeline: events go to a shared-memory log (a global atomic per event costs ~800 clk and distorts
+// the single-threaded issuer), dumped to global memory by CTA 0 at kernel end.  Two writers: epilogue warp 0 lane 0
+// (slot 0) and issuer 0 lane 0 (slot 1), 1024 events each.
 __device__ long long g_t1_trace[8192];
 __device__ int g_t1_trace_n;
-#define TRACE1(ev)                                                                 \
-  do {                                                                             \
-    if (blockIdx.x == 0 && lane == 0) {                                            \
-      const int _i = atomicAdd(&g_t1_trace_n, 1);                                  \
-      if (_i < 4096) { g_t1_trace[2 * _i] = (ev); g_t1_trace[2 * _i + 1] = clock64(); } \
-    }                                                                              \
+#define T1_TRACE_SMEM 24576
+#define TRACE1(ev)                                                                  \
+  do {                                                                              \
+    if (blockIdx.x == 0 && lane == 0 && trace_n < 768) {                           \
+      long long* _t = reinterpret_cast<long long*>(smem + S1_TOTAL) + trace_slot * 1536; \
+      _t[2 * trace_n] = (ev);                                                       \
+      _t[2 * trace_n + 1] = clock64();                                              \
+      trace_n++;                                                                    \
+    }                                                                               \
   } while (0)
 #else
+#define T1_TRACE_SMEM 0
 #define TRACE1(ev) do {} while (0)
 #endif
-
-struct T1Stream {
-  int n_fwd, n_all;
-  uint32_t off[T1_MAXCHUNK];      // byte offset in the blob
-  uint32_t bytes[T1_MAXCHUNK];
-};
 
 struct T1Bars {
   uint64_t w_full[T1_NSLOT];
@@ -227,6 +227,9 @@ k_sdf_tc1(const DevScene sc, const DevNet net, const PointSource src, const uint
   T1Bars* bars = reinterpret_cast<T1Bars*>(smem + S1_BAR);
   float* sw6 = reinterpret_cast<float*>(smem + S1_W6);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int trace_n = 0;
+  const int trace_slot = (warp == 0) ? 0 : 1;
+  (void)trace_n; (void)trace_slot;
   constexpr int NPHASE = GRAD ? 12 : 6;
   const int nch_tile = GRAD ? stream.n_all : stream.n_fwd;
 
@@ -509,7 +512,8 @@ k_sdf_tc1(const DevScene sc, const DevNet net, const PointSource src, const uint
       const uint32_t afeat_lo = (uint32_t)d128 | (tc::smem_u32(smem + S1_AFEAT) >> 4);
       const uint32_t ape_lo = (uint32_t)d128 | (tc::smem_u32(smem + S1_APE) >> 4);
       uint32_t ph_a = 0;
-      int64_t s = 0;
+      int slot = 0;            // ring position / parity kept incrementally (a 64-bit % per chunk costs ~400 clk)
+      uint32_t ring_par = 0;
       for (int64_t it = 0; it < my_tiles; ++it) {
         for (int p = 0; p < NPHASE; ++p) {
           const int nch = t1_phase_chunks(p);
@@ -517,10 +521,11 @@ k_sdf_tc1(const DevScene sc, const DevNet net, const PointSource src, const uint
           ph_a++;
           tc::tc_fence_after();
           if (sub == 0) TRACE1(50 + p);
-          for (int c = 0; c < nch; ++c, ++s) {
+          for (int c = 0; c < nch; ++c, slot = (slot + 1 == T1_NSLOT) ? 0 : slot + 1, ring_par ^= (slot == 0)) {
             if ((c & 1) != sub) continue;
-            const int slot = (int)(s % T1_NSLOT);
-            tc::mbar_wait(&bars->w_full[slot], (uint32_t)((s / T1_NSLOT) & 1));
+            if (sub == 0) TRACE1(1000 + p * 8 + c);
+            tc::mbar_wait(&bars->w_full[slot], ring_par);
+            if (sub == 0) TRACE1(2000 + p * 8 + c);
             const uint32_t wa = (ring + slot * T1_SLOT_BYTES) >> 4;       // 16-byte units
             const bool first = (c == sub);                                  // first chunk of this accumulator
             if (p < 6) {
@@ -571,6 +576,7 @@ k_sdf_tc1(const DevScene sc, const DevNet net, const PointSource src, const uint
               }
             }
             tc::mma_commit(&bars->w_empty[slot]);
+            if (sub == 0) TRACE1(3000 + p * 8 + c);
           }
           tc::mma_commit(&bars->d_full);
           if (sub == 0) TRACE1(70 + p);
@@ -581,16 +587,27 @@ k_sdf_tc1(const DevScene sc, const DevNet net, const PointSource src, const uint
     // =============================== weight loader ===============================
     if (lane == 0) {
       const int64_t total = my_tiles * nch_tile;
-      for (int64_t s = 0; s < total; ++s) {
-        const int slot = (int)(s % T1_NSLOT);
-        const int cid = (int)(s % nch_tile);
-        if (s >= T1_NSLOT) tc::mbar_wait(&bars->w_empty[slot], (uint32_t)(((s / T1_NSLOT) - 1) & 1));
+      int slot = 0, cid = 0;
+      uint32_t par = 1;          // parity of the previous use of this slot (first round: nothing to wait for)
+      for (int64_t s = 0; s < total; ++s, slot = (slot + 1 == T1_NSLOT) ? 0 : slot + 1, par ^= (slot == 0),
+                   cid = (cid + 1 == nch_tile) ? 0 : cid + 1) {
+        if (s >= T1_NSLOT) tc::mbar_wait(&bars->w_empty[slot], par);
         tc::mbar_arrive_expect_tx(&bars->w_full[slot], stream.bytes[cid]);
         tc::bulk_g2s(smem + S1_RING + slot * T1_SLOT_BYTES, wblob + stream.off[cid], stream.bytes[cid],
                      &bars->w_full[slot]);
       }
     }
   }
+#ifdef TC_TRACE
+  if (blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == T1_EPI_WARPS)) {
+    const long long* _t = reinterpret_cast<const long long*>(smem + S1_TOTAL) + trace_slot * 1536;
+    const int base = atomicAdd(&g_t1_trace_n, trace_n);
+    for (int i = 0; i < trace_n && base + i < 4096; ++i) {
+      g_t1_trace[2 * (base + i)] = _t[2 * i];
+      g_t1_trace[2 * (base + i) + 1] = _t[2 * i + 1];
+    }
+  }
+#endif
   tc::tc_fence_before();
   __syncthreads();
   if (warp == T1_EPI_WARPS) tc::tmem_dealloc<512>(tbase);
@@ -611,7 +628,7 @@ static inline float t1_h2f(uint16_t b) {
   return __half2float(h);
 }
 
-static T1Stream g_t1_stream;     // identical for every net of the supported shape; filled at build time
+T1Stream g_t1_stream;            // identical for every net of the supported shape; filled at build time
 
 int surf_build_tc1_weights(const std::vector<std::vector<float>>& W, const surf_net_inputs* in, surf_net* net,
                            cudaStream_t st, int (*dev_alloc)(surf_net*, void**, size_t)) {
@@ -704,8 +721,8 @@ int launch_sdf_tc1(const surf_scene* s, const surf_net* n, const PointSource& sr
                    bool negate, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    SURF_CUDA(cudaFuncSetAttribute(k_sdf_tc1<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, S1_TOTAL));
-    SURF_CUDA(cudaFuncSetAttribute(k_sdf_tc1<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, S1_TOTAL));
+    SURF_CUDA(cudaFuncSetAttribute(k_sdf_tc1<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, S1_TOTAL + T1_TRACE_SMEM));
+    SURF_CUDA(cudaFuncSetAttribute(k_sdf_tc1<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, S1_TOTAL + T1_TRACE_SMEM));
     attr_set = true;
   }
   if (src.n <= 0) return 0;
@@ -713,10 +730,10 @@ int launch_sdf_tc1(const surf_scene* s, const surf_net* n, const PointSource& sr
   const int grid = (int)(tiles < n->n_sm ? tiles : n->n_sm);
   surf_time_begin(d_grad ? 0 : 1, st);
   if (d_grad) {
-    k_sdf_tc1<true><<<grid, T1_THREADS, S1_TOTAL, st>>>(s->dev, n->dev, src, n->tc1_blob, g_t1_stream, d_sdf, d_grad,
+    k_sdf_tc1<true><<<grid, T1_THREADS, S1_TOTAL + T1_TRACE_SMEM, st>>>(s->dev, n->dev, src, n->tc1_blob, g_t1_stream, d_sdf, d_grad,
                                                         (uint4*)n->tc1_scratch, (negate ? 1 : 0) | (surf_mlp_mode() == 4 ? 2 : 0));
   } else {
-    k_sdf_tc1<false><<<grid, T1_THREADS, S1_TOTAL, st>>>(s->dev, n->dev, src, n->tc1_blob, g_t1_stream, d_sdf, nullptr,
+    k_sdf_tc1<false><<<grid, T1_THREADS, S1_TOTAL + T1_TRACE_SMEM, st>>>(s->dev, n->dev, src, n->tc1_blob, g_t1_stream, d_sdf, nullptr,
                                                          (uint4*)n->tc1_scratch, (negate ? 1 : 0) | (surf_mlp_mode() == 4 ? 2 : 0));
   }
   surf_time_end(d_grad ? 0 : 1, st);

@@ -1,0 +1,766 @@
+// K2a + K3, tensor-core edition with the MMA stream pipelined against the epilogue, one 128-point tile per CTA pass:
+// SDF MLP forward + analytic input gradient.
+//   reference: SDFNetworkSparse.sdf / .gradient (sdf_network.py:95-141), lookup_sparse_volume (projector.py:217-390)
+//
+// sdf_tc1.cu runs every layer as "all MMAs, then all of the epilogue": the tensor pipe idles during the epilogue and
+// the 16 epilogue warps idle during the MMAs (tools/trace_t1.py: ~3.5 k clk + ~3.3 k clk per forward layer).  Here
+// the two overlap inside ONE tile:
+//   * the layer accumulators alternate between two TMEM buffers D0 [0,160) / D1 [160,320) (layer phase p uses
+//     D[p & 1]), so layer p+1 may accumulate while the epilogue still reads layer p;
+//   * the epilogue walks the 128 output columns in four groups of 32, ALL 16 warps working on the same group
+//     (warp (q, part): TMEM lane quarter q, columns g*32 + part*8 .. +7), and signals `a_grp[g]` as soon as group g
+//     of the next A operand (fp16 hi [320,384) / lo [384,448)) is in TMEM;
+//   * K chunk g of layer p+1 (K = 32 = exactly those columns) is issued as soon as a_grp[g] fires; the feature /
+//     bias chunks of a forward layer do not depend on the previous layer at all and go first.
+// One thread issues every MMA, in a fixed order, into one accumulator per layer: results are bitwise deterministic.
+// Weight stream, hi/lo fp16 split (3 MMAs per product), u-code scratch for softplus': as sdf_tc1.cu.
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "surf_internal.cuh"
+#include "tc_common.cuh"
+
+#define T2_EPI_WARPS 16
+#define T2_EPI_THREADS (T2_EPI_WARPS * 32)
+#define T2_THREADS ((T2_EPI_WARPS + 2) * 32)     // + 1 MMA issuer + 1 weight loader
+#define T2_SLOT_BYTES 20480                      // N = 160 x K = 32 x (hi + lo)
+#define T2_NSLOT 7
+
+#define T2_D0 0u
+#define T2_D1 160u
+#define T2_AHI 320u
+#define T2_ALO 384u
+
+// dynamic smem (bytes)
+#define S2_RING 0
+#define S2_AFEAT (S2_RING + T2_NSLOT * T2_SLOT_BYTES)      // hi 8 KB | lo 8 KB  (128 rows x K 32)
+#define S2_APE (S2_AFEAT + 16384)
+#define S2_W6 (S2_APE + 16384)                             // 160 floats
+#define S2_PART (S2_W6 + 640)                              // [4][128] floats
+#define S2_GPE (S2_PART + 2048)                            // [28][128] floats
+#define S2_GF (S2_GPE + 14336)                             // [28][128] floats ; later [4][3][128] partial grads
+#define S2_BAR (S2_GF + 14336)
+#define S2_TOTAL (S2_BAR + 256)
+
+#ifdef TC_TRACE
+// in-kernel timeline of CTA 0 (shared-memory log, dumped at kernel end): epilogue warp 0 lane 0 -> slot 0,
+// issuer lane 0 -> slot 1, epilogue warp 15 lane 0 -> slot 2
+__device__ long long g_t2_trace[8192];
+__device__ int g_t2_trace_n;
+#define T2_TRACE_SMEM 24576
+#define TRACE2(ev)                                                                  \
+  do {                                                                              \
+    if (blockIdx.x == 0 && lane == 0 && trace_slot >= 0 && trace_n < 512) {        \
+      long long* _t = reinterpret_cast<long long*>(smem + S2_TOTAL) + trace_slot * 1024; \
+      _t[2 * trace_n] = (ev);                                                       \
+      _t[2 * trace_n + 1] = clock64();                                              \
+      trace_n++;                                                                    \
+    }                                                                               \
+  } while (0)
+#else
+#define T2_TRACE_SMEM 0
+#define TRACE2(ev) do {} while (0)
+#endif
+
+struct T2Bars {
+  uint64_t w_full[T2_NSLOT];
+  uint64_t w_empty[T2_NSLOT];
+  uint64_t d_full;          // all MMAs of a layer phase done (tcgen05.commit of the issuer)
+  uint64_t stage_ready;     // a tile's smem operands (features, PE) staged: one arrival per epilogue warp
+  uint64_t a_grp[4];        // column group g of the next A operand written: one arrival per epilogue warp
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ float t2_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float t2_lg2(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float t2_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// softplus(beta = 100), branch-free: max(z, 0) + log1p(e) / 100 with e = exp(-|100 z|) in (0, 1].
+// softplus'(z) = sigmoid(100 z) = z >= 0 ? 1 / (1 + e) : 1 - 1 / (1 + e).  For the reverse pass the forward epilogue
+// parks e as a 16-bit fixed-point code plus the sign of z (no F2I: min(e, 1 - 2^-16) + 128.0f has ulp 2^-16, the
+// adder's round-to-nearest leaves round(e * 65536) in the low 16 bits of the word).
+__device__ __forceinline__ float t2_softplus(float z, float& e) {
+  e = t2_ex2(fabsf(z) * -144.26950408889634f);
+  return fmaf(t2_lg2(1.0f + e), 0.0069314718055994531f, fmaxf(z, 0.f));
+}
+__device__ __forceinline__ uint32_t t2_code_word(float e) { return __float_as_uint(fminf(e, 0.9999847412109375f) + 128.0f); }
+// pair word (two codes) -> u = 1 + e of element t
+template <int T>
+__device__ __forceinline__ float t2_decode_u(uint32_t pair) {
+  return __uint_as_float(__byte_perm(pair, 0x43000000u, T ? 0x7632 : 0x7610)) - 127.0f;
+}
+
+// chunks per layer phase of the weight stream: phases 0..5 forward, 6..10 reverse lin5..lin1, 11 reverse lin0
+__device__ __forceinline__ int t2_phase_chunks(int phase) {
+  if (phase == 0) return 1;
+  if (phase < 6) return 6;      // 2 x K16 (features | bias) first, then 4 x K32 hidden
+  if (phase < 11) return 4;
+  return 2;
+}
+
+struct T2Epi {
+  uint32_t tl;            // TMEM base of my lane quarter
+  int part, r, te;
+  const uint8_t* ape;
+  const float* sw6;
+  float inv_scale;
+  uint4* scratch;
+  uint32_t* sgn_scratch;
+  float* s_gpe;
+  int dbg;                // timing experiments (SURF_T2_DEBUG): 8 = skip the activation math, 16 = skip the code scratch
+};
+
+__device__ __forceinline__ float t2_get_k(const uint8_t* base, int r, int k) {
+  const uint32_t off = (uint32_t)(k >> 3) * 2048u + r * 16 + (k & 7) * 2;
+  return __half2float(*reinterpret_cast<const __half*>(base + off)) +
+         __half2float(*reinterpret_cast<const __half*>(base + 8192 + off));
+}
+
+// Forward activation of my 8 columns cb .. cb+7 of one group: h = softplus(z).  SKIP: 0 = plain hidden columns;
+// 1 = columns 5..7 of my 8 are positional-encoding inputs of the skip layer (cb == 96); 2 = all 8 are.  HEAD: lin5 ->
+// SDF head partial sum and (GRAD) h = delta5 = w6 / scale * softplus', the first reverse A operand.
+template <bool GRAD, int SKIP, bool HEAD>
+__device__ __forceinline__ void t2_fwd_act(const T2Epi& c, int cb, const uint32_t (&d)[8], float (&h)[8], uint4& spw,
+                                           uint32_t& sgn, float& head) {
+  uint32_t cw[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+#pragma unroll
+  for (int n = 0; n < 8; ++n) {
+    const bool pe = (SKIP == 2) || (SKIP == 1 && n >= 5);
+    const float z = __uint_as_float(d[n]);
+    if (pe) {
+      h[n] = t2_get_k(c.ape, c.r, cb + n - 101);
+      if (GRAD) sgn = __funnelshift_l(0x80000000u, sgn, 1);
+    } else {
+      float e;
+      h[n] = t2_softplus(z, e);
+      if (HEAD) {
+        const float w = c.sw6[cb + n];
+        head = fmaf(h[n], w, head);
+        if (GRAD) {
+          const float rr = t2_rcp(1.0f + e);
+          h[n] = w * c.inv_scale * (z >= 0.f ? rr : 1.0f - rr);
+        }
+      } else if (GRAD) {
+        cw[n] = t2_code_word(e);
+        sgn = __funnelshift_l(__float_as_uint(z), sgn, 1);      // element e of the layer ends at bit 31 - e
+      }
+    }
+  }
+  if (GRAD && !HEAD)
+    spw = make_uint4(__byte_perm(cw[0], cw[1], 0x5410), __byte_perm(cw[2], cw[3], 0x5410), __byte_perm(cw[4], cw[5], 0x5410),
+                     __byte_perm(cw[6], cw[7], 0x5410));
+}
+
+// Reverse activation of my 8 columns of one group: v = delta_{l-1} = D * softplus'(z_{l-1}); the sign of element n is
+// bit 31 - n of `sgn`.  SKIP as above: those columns are the PE input gradient of the skip layer (kept in smem, v = 0).
+template <int SKIP>
+__device__ __forceinline__ void t2_bwd_act(const T2Epi& c, int cb, const uint32_t (&d)[8], const uint4& spw, uint32_t sgn,
+                                           float (&v)[8]) {
+  const uint32_t sp[4] = {spw.x, spw.y, spw.z, spw.w};
+#pragma unroll
+  for (int n = 0; n < 8; ++n) {
+    const bool pe = (SKIP == 2) || (SKIP == 1 && n >= 5);
+    const float g = __uint_as_float(d[n]);
+    if (pe) {
+      c.s_gpe[(cb + n - 101) * 128 + c.r] = g;
+      v[n] = 0.f;
+    } else {
+      const float rr = t2_rcp((n & 1) ? t2_decode_u<1>(sp[n >> 1]) : t2_decode_u<0>(sp[n >> 1]));
+      const bool neg = ((sgn >> (31 - n)) & 1u) != 0u;
+      v[n] = g * (neg ? 1.0f - rr : rr);
+    }
+  }
+}
+
+// my 8 columns of the next A operand -> TMEM as fp16 hi / lo
+__device__ __forceinline__ void t2_store_a(const T2Epi& c, int cb, const float (&h)[8]) {
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) tc::split2(h[2 * j], h[2 * j + 1], hi[j], lo[j]);
+  tc::tmem_st4(c.tl + T2_AHI + (cb >> 1), hi);
+  tc::tmem_st4(c.tl + T2_ALO + (cb >> 1), lo);
+}
+
+// group g of the next A operand is in TMEM: one arrival per warp
+__device__ __forceinline__ void t2_signal_group(uint64_t* bar, int lane) {
+  tc::tmem_wait_st();
+  tc::tc_fence_before();
+  __syncwarp();
+  if (lane == 0) tc::mbar_arrive(bar);
+}
+
+// wait for the outstanding tcgen05.ld; the registers it fills are operands so that no use can be scheduled above it
+__device__ __forceinline__ void t2_wait_ld(uint32_t (&r)[8]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7])
+               :
+               : "memory");
+}
+
+// The group loops below are deliberately NOT unrolled: inside one basic block ptxas hoists the MUFU work of all four
+// groups to the front and the first group would be signalled when half of the layer is done (measured).  They are
+// software-pipelined by hand instead: the accumulator columns of group g+1 are requested before group g is computed,
+// and group g-1 is signalled (tcgen05.wait::st + arrive) after the MUFU part of group g, when its TMEM stores have long
+// landed — a warp never sits on a TMEM round trip with nothing to issue.
+template <bool GRAD, bool HEAD>
+__device__ __forceinline__ void t2_fwd_layer(const T2Epi& c, T2Bars* bars, int l, bool skip_next, float& head, int lane,
+                                             uint8_t* smem, int& trace_n, int trace_slot) {
+  const uint32_t dcol = c.tl + ((l & 1) ? T2_D1 : T2_D0) + c.part * 8;
+  constexpr bool SIGNAL = !HEAD || GRAD;
+  uint32_t sgn = 0;
+  uint32_t dn[8];
+  tc::tmem_ld8(dcol, dn);
+#pragma unroll 1
+  for (int g = 0; g < 4; ++g) {
+    t2_wait_ld(dn);
+    uint32_t dv[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dv[j] = dn[j];
+    if (g < 3) tc::tmem_ld8(dcol + (g + 1) * 32, dn);
+    TRACE2(6000 + l * 16 + g * 4);
+    const int cb = g * 32 + c.part * 8;
+    uint4 spw = make_uint4(0u, 0u, 0u, 0u);
+    float h[8];
+    if (!HEAD && g == 3 && skip_next) {
+      if (c.part == 0) t2_fwd_act<GRAD, 1, false>(c, cb, dv, h, spw, sgn, head);
+      else t2_fwd_act<GRAD, 2, false>(c, cb, dv, h, spw, sgn, head);
+    } else if (c.dbg & 8) {
+#pragma unroll
+      for (int n = 0; n < 8; ++n) h[n] = __uint_as_float(dv[n]);
+    } else {
+      t2_fwd_act<GRAD, 0, HEAD>(c, cb, dv, h, spw, sgn, head);
+    }
+    TRACE2(6000 + l * 16 + g * 4 + 1);
+    if (SIGNAL && g > 0) t2_signal_group(&bars->a_grp[g - 1], lane);
+    if (SIGNAL) t2_store_a(c, cb, h);
+    TRACE2(6000 + l * 16 + g * 4 + 2);
+    if (GRAD && !HEAD && !(c.dbg & 16)) c.scratch[(size_t)(l * 4 + g) * T2_EPI_THREADS + c.te] = spw;
+  }
+  if (SIGNAL) t2_signal_group(&bars->a_grp[3], lane);
+  if (GRAD && !HEAD) c.sgn_scratch[(size_t)l * T2_EPI_THREADS + c.te] = sgn;
+}
+
+// reverse layer phase p: D[p & 1] holds d sdf / d (input of lin_l), columns 128.. the feature-gradient part;
+// lsrc = l - 1: the layer whose softplus' codes apply
+__device__ __forceinline__ void t2_bwd_layer(const T2Epi& c, T2Bars* bars, int p, bool skip_pe, int lsrc, float (&gf)[8],
+                                             int lane, uint8_t* smem, int& trace_n, int trace_slot) {
+  const uint32_t dbase = c.tl + ((p & 1) ? T2_D1 : T2_D0) + c.part * 8;
+  uint32_t sgn = c.sgn_scratch[(size_t)lsrc * T2_EPI_THREADS + c.te];
+  uint4 spw = c.scratch[(size_t)(lsrc * 4) * T2_EPI_THREADS + c.te];
+  uint32_t dn[8];
+  tc::tmem_ld8(dbase, dn);
+#pragma unroll 1
+  for (int g = 0; g < 4; ++g) {
+    t2_wait_ld(dn);
+    uint32_t dv[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dv[j] = dn[j];
+    tc::tmem_ld8(dbase + (g + 1) * 32, dn);               // g == 3: the feature-gradient columns 128 + part*8 ..
+    TRACE2(6000 + p * 16 + g * 4);
+    const uint4 spw_cur = spw;
+    if (g < 3 && !(c.dbg & 16)) spw = c.scratch[(size_t)(lsrc * 4 + g + 1) * T2_EPI_THREADS + c.te];     // next group's codes
+    const int cb = g * 32 + c.part * 8;
+    float v[8];
+    if (g == 3 && skip_pe) {
+      if (c.part == 0) t2_bwd_act<1>(c, cb, dv, spw_cur, sgn, v);
+      else t2_bwd_act<2>(c, cb, dv, spw_cur, sgn, v);
+    } else if (c.dbg & 8) {
+#pragma unroll
+      for (int n = 0; n < 8; ++n) v[n] = __uint_as_float(dv[n]);
+    } else {
+      t2_bwd_act<0>(c, cb, dv, spw_cur, sgn, v);
+    }
+    TRACE2(6000 + p * 16 + g * 4 + 1);
+    if (g > 0) t2_signal_group(&bars->a_grp[g - 1], lane);
+    t2_store_a(c, cb, v);
+    TRACE2(6000 + p * 16 + g * 4 + 2);
+    sgn <<= 8;
+  }
+  t2_signal_group(&bars->a_grp[3], lane);
+  t2_wait_ld(dn);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) gf[j] += __uint_as_float(dn[j]);
+}
+
+
+template <bool GRAD>
+__global__ void __launch_bounds__(T2_THREADS, 1)
+k_sdf_tc2(const DevScene sc, const DevNet net, const PointSource src, const uint8_t* __restrict__ wblob,
+          const T1Stream stream, float* __restrict__ sdf_out, float* __restrict__ grad_out,
+          uint4* __restrict__ scratch_all, int flags) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  T2Bars* bars = reinterpret_cast<T2Bars*>(smem + S2_BAR);
+  float* sw6 = reinterpret_cast<float*>(smem + S2_W6);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int trace_n = 0;
+  const int trace_slot = (warp == 0) ? 0 : (warp == T2_EPI_WARPS ? 1 : (warp == 15 ? 2 : -1));
+  (void)trace_n; (void)trace_slot;
+  const int nch_tile = GRAD ? stream.n_all : stream.n_fwd;
+
+  int64_t n_total = src.n;
+  if (src.count) {
+    const int64_t c = *src.count;
+    n_total = c < n_total ? c : n_total;
+  }
+  const int64_t n_tiles = (n_total + 127) / 128;
+  int64_t my_tiles = 0;
+  if ((int64_t)blockIdx.x < n_tiles) my_tiles = (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+
+  if (warp == T2_EPI_WARPS) tc::tmem_alloc<512>(&bars->tmem_base);
+  if (tid == 0) {
+    for (int i = 0; i < T2_NSLOT; ++i) {
+      tc::mbar_init(&bars->w_full[i], 1);
+      tc::mbar_init(&bars->w_empty[i], 1);
+    }
+    tc::mbar_init(&bars->d_full, 1);
+    tc::mbar_init(&bars->stage_ready, T2_EPI_WARPS);
+    for (int g = 0; g < 4; ++g) tc::mbar_init(&bars->a_grp[g], T2_EPI_WARPS);
+    tc::mbar_fence_init();
+  }
+  for (int i = tid; i < 160; i += T2_THREADS) sw6[i] = net.w6[i];
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tbase = bars->tmem_base;
+
+  if (warp < T2_EPI_WARPS) {
+    // =============================== epilogue / staging warps ===============================
+    const int q = warp & 3, part = warp >> 2;
+    const int r = q * 32 + lane;                 // row = point = TMEM lane
+    const uint32_t tl = tbase + ((uint32_t)(q * 32) << 16);
+    uint8_t* afeat = smem + S2_AFEAT;
+    uint8_t* ape = smem + S2_APE;
+    float* s_part = reinterpret_cast<float*>(smem + S2_PART);
+    float* s_gpe = reinterpret_cast<float*>(smem + S2_GPE);
+    float* s_gf = reinterpret_cast<float*>(smem + S2_GF);
+    uint4* scratch = scratch_all + (size_t)blockIdx.x * (5 * 4 * T2_EPI_THREADS + 5 * T2_EPI_THREADS / 4);
+    uint32_t* sgn_scratch = reinterpret_cast<uint32_t*>(scratch + 5 * 4 * T2_EPI_THREADS);
+    const int te = warp * 32 + lane;             // 0..511
+    uint32_t ph_d = 0;
+    auto put_k = [&](uint8_t* base, int k, float v) {
+      const __half h = __float2half_rn(v);
+      const __half l = __float2half_rn(v - __half2float(h));
+      const uint32_t off = (uint32_t)(k >> 3) * 2048u + r * 16 + (k & 7) * 2;
+      *reinterpret_cast<__half*>(base + off) = h;
+      *reinterpret_cast<__half*>(base + 8192 + off) = l;
+    };
+    auto get_k = [&](const uint8_t* base, int k) { return t2_get_k(base, r, k); };
+    auto epi_bar = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(T2_EPI_THREADS) : "memory"); };
+    auto load_point = [&](int64_t i, float& px, float& py, float& pz) -> int64_t {
+      px = 0.f; py = 0.f; pz = 0.f;
+      if (i >= n_total) return -1;
+      const int64_t id = src.list ? (int64_t)src.list[i] : i;
+      if (src.mode == 0) {
+        px = src.pts[id * 3]; py = src.pts[id * 3 + 1]; pz = src.pts[id * 3 + 2];
+      } else if (src.mode == 1) {
+        const int64_t ray = id / src.S;
+        const float t = src.mid_z[id];
+        px = ray_at(src.rays_o[ray * 3], src.rays_d[ray * 3], t);
+        py = ray_at(src.rays_o[ray * 3 + 1], src.rays_d[ray * 3 + 1], t);
+        pz = ray_at(src.rays_o[ray * 3 + 2], src.rays_d[ray * 3 + 2], t);
+      } else {
+        const int64_t yz = (int64_t)src.ny * src.nz;
+        const int xi = (int)(id / yz);
+        const int rem = (int)(id - (int64_t)xi * yz);
+        px = src.xs[xi]; py = src.ys[rem / src.nz]; pz = src.zs[rem % src.nz];
+      }
+      return id;
+    };
+
+    T2Epi ec;
+    ec.tl = tl; ec.part = part; ec.r = r; ec.te = te; ec.ape = ape; ec.sw6 = sw6; ec.inv_scale = net.inv_scale;
+    ec.scratch = scratch; ec.sgn_scratch = sgn_scratch; ec.s_gpe = s_gpe; ec.dbg = flags;
+
+    float nf7[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // next tile's features of (row, level = part), gathered early
+    bool have_next = false;
+    for (int64_t it = 0; it < my_tiles; ++it) {
+      const int64_t tile = (int64_t)blockIdx.x + it * gridDim.x;
+      float px, py, pz;
+      const int64_t id = load_point(tile * 128 + r, px, py, pz);
+      // ---- staging: thread (row, part) gathers level `part` and encodes PE frequency `part` ----
+      {
+        float f7[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (GRAD && have_next) {
+#pragma unroll
+          for (int c = 0; c < 7; ++c) f7[c] = nf7[c];
+        } else if (part < sc.n_levels && !(flags & 64)) {
+          sparse_level<0>(sc, part, px, py, pz, nullptr, f7);
+        }
+#pragma unroll
+        for (int c = 0; c < 7; ++c) put_k(afeat, part * 7 + c, f7[c]);
+        const float xs[3] = {px * net.scale, py * net.scale, pz * net.scale};
+        if (part == 0) {
+#pragma unroll
+          for (int d = 0; d < 3; ++d) put_k(ape, d, xs[d]);
+        }
+        if (part == 3) {
+          put_k(afeat, 28, 1.0f);
+          put_k(ape, 27, 1.0f);
+#pragma unroll
+          for (int k = 29; k < 32; ++k) put_k(afeat, k, 0.f);
+#pragma unroll
+          for (int k = 28; k < 32; ++k) put_k(ape, k, 0.f);
+        }
+        const float fr = (float)(1 << part);
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          float sn = 0.f, cs = 0.f;
+          if (part < net.multires) sincosf(xs[d] * fr, &sn, &cs);
+          put_k(ape, 3 + 6 * part + d, sn);
+          put_k(ape, 3 + 6 * part + 3 + d, cs);
+        }
+      }
+      tc::fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&bars->stage_ready);
+      if (warp == 0) TRACE2(1);
+
+      float gf[8];          // reverse pass: d sdf / d feat for feature columns part*8 .. part*8+7
+      // ------------------------------------ forward ------------------------------------
+      for (int l = 0; l < 6; ++l) {
+        if (l == 1 && it + 1 < my_tiles && part < sc.n_levels) {
+          // while the tensor core works on this layer: pull the NEXT tile's gather working set into L2
+          float nx, ny, nz;
+          if (load_point((tile + gridDim.x) * 128 + r, nx, ny, nz) >= 0 && !(flags & 64)) sparse_prefetch_l2(sc, part, nx, ny, nz);
+        }
+        tc::mbar_wait(&bars->d_full, ph_d & 1);
+        ph_d++;
+        tc::tc_fence_after();
+        TRACE2(10 + l);
+        float head = 0.f;
+        if (l < 5) t2_fwd_layer<GRAD, false>(ec, bars, l, l + 1 == net.skip_layer, head, lane, smem, trace_n, trace_slot);
+        else t2_fwd_layer<GRAD, true>(ec, bars, l, false, head, lane, smem, trace_n, trace_slot);
+        if (warp == 0) TRACE2(30 + l);
+        if (l == 5) {
+          s_part[part * 128 + r] = head;
+          epi_bar();
+          if (part == 0) {
+            float s = s_part[r] + s_part[128 + r] + s_part[256 + r] + s_part[384 + r] + net.b6;
+#pragma unroll
+            for (int c = 0; c < 28; ++c) s = fmaf(get_k(afeat, c), sw6[128 + c], s);
+            s *= net.inv_scale;
+            if (id >= 0) sdf_out[id] = (flags & 1) ? -s : s;
+          }
+          if (!GRAD) {
+            tc::tc_fence_before();
+            epi_bar();            // afeat / s_part reads done before the next tile restages
+          }
+        }
+      }
+      if (!GRAD) continue;
+
+      // ------------------------------------ reverse ------------------------------------
+#pragma unroll
+      for (int j = 0; j < 8; ++j) gf[j] = sw6[128 + part * 8 + j] * net.inv_scale;
+      for (int l = 5; l >= 1; --l) {
+        if (l == 4) {
+          // gather the NEXT tile's features now (its lines were prefetched into L2 during lin1): the load latency
+          // hides behind this layer's MMAs and the next tile's staging shrinks to the smem writes
+          have_next = false;
+          if (it + 1 < my_tiles) {
+            float nx, ny, nz;
+            load_point((tile + gridDim.x) * 128 + r, nx, ny, nz);
+#pragma unroll
+            for (int c = 0; c < 7; ++c) nf7[c] = 0.f;
+            if (part < sc.n_levels && !(flags & 64)) sparse_level<0>(sc, part, nx, ny, nz, nullptr, nf7);
+            have_next = true;
+          }
+        }
+        tc::mbar_wait(&bars->d_full, ph_d & 1);
+        ph_d++;
+        tc::tc_fence_after();
+        TRACE2(16 + (5 - l));
+        t2_bwd_layer(ec, bars, 11 - l, l == net.skip_layer, l - 1, gf, lane, smem, trace_n, trace_slot);
+        if (warp == 0) TRACE2(36 + (5 - l));
+      }
+      // feature gradients -> smem (28 x 128)
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (part * 8 + j < 28) s_gf[(part * 8 + j) * 128 + r] = gf[j];
+      epi_bar();                                   // s_gpe (skip part) and s_gf complete
+      // d feats / d x for level `part` (re-gather; lines were touched a tile ago, L2 hits) — issued before
+      // waiting for the lin0 reverse MMAs so its latency overlaps them
+      float o3[3] = {0.f, 0.f, 0.f};
+      if (part < sc.n_levels && !(flags & 64)) {
+        float g7[7];
+#pragma unroll
+        for (int c = 0; c < 7; ++c) g7[c] = s_gf[(part * 7 + c) * 128 + r];
+        sparse_level<1>(sc, part, px, py, pz, g7, o3);
+      }
+      // ---- reverse of lin0: g_pe += delta0 . W0 (N = 32), phase 11 -> D1 ----
+      tc::mbar_wait(&bars->d_full, ph_d & 1);
+      ph_d++;
+      tc::tc_fence_after();
+      if (part == 0) {
+        uint32_t a[16];
+#pragma unroll
+        for (int hb = 0; hb < 2; ++hb) {
+          tc::tmem_ld16(tl + T2_D1 + hb * 16, a);
+          tc::tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int k = hb * 16 + j;
+            if (k < 27) s_gpe[k * 128 + r] += __uint_as_float(a[j]);
+          }
+        }
+      }
+      tc::tc_fence_before();
+      epi_bar();                                   // all s_gf reads done, s_gpe final
+      float* s_pg = s_gf;                          // reuse as [4][3][128]
+      s_pg[(part * 3 + 0) * 128 + r] = o3[0];
+      s_pg[(part * 3 + 1) * 128 + r] = o3[1];
+      s_pg[(part * 3 + 2) * 128 + r] = o3[2];
+      epi_bar();
+      if (part < 3 && id >= 0) {                   // thread (row, d = part) finishes component d
+        const int d = part;
+        float gx = s_gpe[d * 128 + r];
+        float fr = 1.0f;
+        for (int f = 0; f < net.multires; ++f) {
+          const float sn = get_k(ape, 3 + 6 * f + d), cs = get_k(ape, 3 + 6 * f + 3 + d);
+          gx += fr * (s_gpe[(3 + 6 * f + d) * 128 + r] * cs - s_gpe[(3 + 6 * f + 3 + d) * 128 + r] * sn);
+          fr *= 2.0f;
+        }
+        gx *= net.scale;
+#pragma unroll
+        for (int lv = 0; lv < 4; ++lv) gx += s_pg[(lv * 3 + d) * 128 + r];
+        grad_out[id * 3 + d] = gx;
+      }
+      epi_bar();                                   // smem scratch free for the next tile
+      if (warp == 0) TRACE2(99);
+    }
+  } else if (warp == T2_EPI_WARPS) {
+    // =============================== the MMA issuer ===============================
+    const bool fast = (flags & 2) != 0;       // single fp16 MMA per product (opt-in reduced-precision mode)
+    const bool nomma = (flags & 4) != 0;      // timing experiment: skip the tcgen05.mma instructions (results invalid)
+    if (lane == 0) {
+      const uint32_t ring = tc::smem_u32(smem + S2_RING);
+      const uint32_t tAhi = tbase + T2_AHI, tAlo = tbase + T2_ALO;
+      const uint32_t id128 = tc::idesc_f16(128, 128, 0), id160 = tc::idesc_f16(128, 160, 0), id32 = tc::idesc_f16(128, 32, 0);
+      // descriptor constant parts: SBO 128; LBO = rows * 16
+      const uint64_t d128 = tc::smem_desc_kmajor(0, 2048, 128), d160 = tc::smem_desc_kmajor(0, 2560, 128),
+                     d32 = tc::smem_desc_kmajor(0, 512, 128);
+      const uint32_t afeat_lo = (uint32_t)d128 | (tc::smem_u32(smem + S2_AFEAT) >> 4);
+      const uint32_t ape_lo = (uint32_t)d128 | (tc::smem_u32(smem + S2_APE) >> 4);
+      const uint32_t dh128 = (uint32_t)(d128 >> 32), dh160 = (uint32_t)(d160 >> 32), dh32 = (uint32_t)(d32 >> 32);
+      uint32_t ph_stage = 0, ph_grp = 0;
+      int slot = 0;
+      uint32_t ring_par = 0;
+      // wait for the next weight chunk; returns its smem address in 16-byte units
+      auto next_chunk = [&]() -> uint32_t {
+        tc::mbar_wait(&bars->w_full[slot], ring_par);
+        return (ring + slot * T2_SLOT_BYTES) >> 4;
+      };
+      auto release_chunk = [&]() {
+        tc::mma_commit(&bars->w_empty[slot]);
+        slot = (slot + 1 == T2_NSLOT) ? 0 : slot + 1;
+        ring_par ^= (slot == 0);
+      };
+      for (int64_t it = 0; it < my_tiles; ++it) {
+        // ---- phase 0: lin0 on the positional encoding (A in smem) -> D0 ----
+        tc::mbar_wait(&bars->stage_ready, ph_stage & 1);
+        ph_stage++;
+        tc::tc_fence_after();
+        TRACE2(50);
+        {
+          const uint32_t tD = tbase + T2_D0;
+          const uint32_t w0 = (uint32_t)d128 | next_chunk(), dh = dh128, a0 = ape_lo;
+          if (!nomma) tc::mma_ss_w<false>(tD, a0, dh, w0, dh, id128);
+          if (!nomma) if (!fast) tc::mma_ss_w<true>(tD, a0 + 512, dh, w0, dh, id128);
+          if (!nomma) if (!fast) tc::mma_ss_w<true>(tD, a0, dh, w0 + 512, dh, id128);
+          if (!nomma) tc::mma_ss_w<true>(tD, a0 + 256, dh, w0 + 256, dh, id128);
+          if (!nomma) if (!fast) tc::mma_ss_w<true>(tD, a0 + 768, dh, w0 + 256, dh, id128);
+          if (!nomma) if (!fast) tc::mma_ss_w<true>(tD, a0 + 256, dh, w0 + 768, dh, id128);
+          release_chunk();
+          tc::mma_commit(&bars->d_full);
+          TRACE2(70);
+        }
+        // ---- phases 1..5: lin1..lin5 ----
+        for (int p = 1; p < 6; ++p) {
+          const uint32_t tD = tbase + ((p & 1) ? T2_D1 : T2_D0);
+          const uint32_t dh = dh128;
+          TRACE2(50 + p);
+          // feature | bias columns (A in smem, independent of the previous layer): two K = 16 half chunks
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const uint32_t w0 = (uint32_t)d128 | next_chunk();
+            const uint32_t a0 = afeat_lo + h * 256;
+            if (!nomma) if (h == 0) tc::mma_ss_w<false>(tD, a0, dh, w0, dh, id128); else tc::mma_ss_w<true>(tD, a0, dh, w0, dh, id128);
+            if (!nomma) if (!fast) tc::mma_ss_w<true>(tD, a0 + 512, dh, w0, dh, id128);
+            if (!nomma) if (!fast) tc::mma_ss_w<true>(tD, a0, dh, w0 + 256, dh, id128);
+            release_chunk();
+            TRACE2(4000 + p * 8 + h);
+          }
+          // hidden columns: K chunk c needs column group c of the previous layer's epilogue
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            tc::mbar_wait(&bars->a_grp[c], ph_grp & 1);
+            tc::tc_fence_after();
+            TRACE2(2000 + p * 8 + c);
+            const uint32_t w0 = (uint32_t)d128 | next_chunk();
+            const uint32_t ah = tAhi + c * 16, al = tAlo + c * 16;
+            if (!nomma) tc::mma_ts_w<true>(tD, ah, w0, dh, id128);
+            if (!nomma) if (!fast) tc::mma_ts_w<true>(tD, al, w0, dh, id128);
+            if (!nomma) if (!fast) tc::mma_ts_w<true>(tD, ah, w0 + 512, dh, id128);
+            if (!nomma) tc::mma_ts_w<true>(tD, ah + 8, w0 + 256, dh, id128);
+            if (!nomma) if (!fast) tc::mma_ts_w<true>(tD, al + 8, w0 + 256, dh, id128);
+            if (!nomma) if (!fast) tc::mma_ts_w<true>(tD, ah + 8, w0 + 768, dh, id128);
+            release_chunk();
+          }
+          ph_grp++;
+          tc::mma_commit(&bars->d_full);
+          TRACE2(70 + p);
+        }
+        if (!GRAD) continue;
+        // ---- phases 6..10: reverse of lin5..lin1, N = 160, K chunk c = column group c of delta ----
+        for (int p = 6; p < 11; ++p) {
+          const uint32_t tD = tbase + ((p & 1) ? T2_D1 : T2_D0);
+          const uint32_t dh = dh160;
+          TRACE2(50 + p);
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            tc::mbar_wait(&bars->a_grp[c], ph_grp & 1);
+            tc::tc_fence_after();
+            TRACE2(2000 + p * 8 + c);
+            const uint32_t w0 = (uint32_t)d160 | next_chunk();
+            const uint32_t ah = tAhi + c * 16, al = tAlo + c * 16;
+            if (!nomma) if (c == 0) tc::mma_ts_w<false>(tD, ah, w0, dh, id160); else tc::mma_ts_w<true>(tD, ah, w0, dh, id160);
+            if (!nomma) if (!fast) tc::mma_ts_w<true>(tD, al, w0, dh, id160);
+            if (!nomma) if (!fast) tc::mma_ts_w<true>(tD, ah, w0 + 640, dh, id160);
+            if (!nomma) tc::mma_ts_w<true>(tD, ah + 8, w0 + 320, dh, id160);
+            if (!nomma) if (!fast) tc::mma_ts_w<true>(tD, al + 8, w0 + 320, dh, id160);
+            if (!nomma) if (!fast) tc::mma_ts_w<true>(tD, ah + 8, w0 + 960, dh, id160);
+            release_chunk();
+          }
+          ph_grp++;
+          tc::mma_commit(&bars->d_full);
+          TRACE2(70 + p);
+        }
+        // ---- phase 11: reverse of lin0, N = 32, two K = 64 chunks (column groups 2c, 2c+1) -> D1 ----
+        {
+          const uint32_t tD = tbase + T2_D1;
+          const uint32_t dh = dh32;
+          TRACE2(61);
+#pragma unroll 1
+          for (int c = 0; c < 2; ++c) {
+            tc::mbar_wait(&bars->a_grp[2 * c], ph_grp & 1);
+            tc::mbar_wait(&bars->a_grp[2 * c + 1], ph_grp & 1);
+            tc::tc_fence_after();
+            const uint32_t w0 = (uint32_t)d32 | next_chunk();
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint32_t ah = tAhi + c * 32 + ks * 8, al = tAlo + c * 32 + ks * 8;
+              if (!nomma) if (c == 0 && ks == 0) tc::mma_ts_w<false>(tD, ah, w0, dh, id32); else tc::mma_ts_w<true>(tD, ah, w0 + ks * 64, dh, id32);
+              if (!nomma) if (!fast) tc::mma_ts_w<true>(tD, al, w0 + ks * 64, dh, id32);
+              if (!nomma) if (!fast) tc::mma_ts_w<true>(tD, ah, w0 + 256 + ks * 64, dh, id32);
+            }
+            release_chunk();
+          }
+          ph_grp++;
+          tc::mma_commit(&bars->d_full);
+          TRACE2(81);
+        }
+      }
+    }
+  } else {
+    // =============================== weight loader ===============================
+    if (lane == 0) {
+      const int64_t total = my_tiles * nch_tile;
+      int slot = 0, cid = 0;
+      uint32_t par = 1;          // parity of the previous use of this slot (first round: nothing to wait for)
+      for (int64_t s = 0; s < total; ++s, slot = (slot + 1 == T2_NSLOT) ? 0 : slot + 1, par ^= (slot == 0),
+                   cid = (cid + 1 == nch_tile) ? 0 : cid + 1) {
+        if (s >= T2_NSLOT) tc::mbar_wait(&bars->w_empty[slot], par);
+        if (flags & 32) {           // timing experiment: no weight traffic
+          tc::mbar_arrive(&bars->w_full[slot]);
+          continue;
+        }
+        tc::mbar_arrive_expect_tx(&bars->w_full[slot], stream.bytes[cid]);
+        tc::bulk_g2s(smem + S2_RING + slot * T2_SLOT_BYTES, wblob + stream.off[cid], stream.bytes[cid],
+                     &bars->w_full[slot]);
+      }
+    }
+  }
+#ifdef TC_TRACE
+  if (blockIdx.x == 0 && lane == 0 && trace_slot >= 0) {
+    const long long* _t = reinterpret_cast<const long long*>(smem + S2_TOTAL) + trace_slot * 1024;
+    const int base = atomicAdd(&g_t2_trace_n, trace_n);
+    for (int i = 0; i < trace_n && base + i < 4096; ++i) {
+      g_t2_trace[2 * (base + i)] = _t[2 * i] + 100000ll * trace_slot;
+      g_t2_trace[2 * (base + i) + 1] = _t[2 * i + 1];
+    }
+  }
+#endif
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == T2_EPI_WARPS) tc::tmem_dealloc<512>(tbase);
+}
+
+// the weight stream of sdf_tc1.cu with the feature | bias half chunks of every forward layer moved to the front
+static T1Stream t2_reordered_stream() {
+  T1Stream S = g_t1_stream;
+  for (int l = 1; l < 6; ++l) {
+    const int base = 1 + (l - 1) * 6;
+    const int order[6] = {4, 5, 0, 1, 2, 3};
+    for (int c = 0; c < 6; ++c) {
+      S.off[base + c] = g_t1_stream.off[base + order[c]];
+      S.bytes[base + c] = g_t1_stream.bytes[base + order[c]];
+    }
+  }
+  return S;
+}
+
+int launch_sdf_tc2(const surf_scene* s, const surf_net* n, const PointSource& src, float* d_sdf, float* d_grad,
+                   bool negate, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    SURF_CUDA(cudaFuncSetAttribute(k_sdf_tc2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, S2_TOTAL + T2_TRACE_SMEM));
+    SURF_CUDA(cudaFuncSetAttribute(k_sdf_tc2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, S2_TOTAL + T2_TRACE_SMEM));
+    attr_set = true;
+  }
+  if (src.n <= 0) return 0;
+  const T1Stream stream = t2_reordered_stream();
+  const int64_t tiles = (src.n + 127) / 128;
+  const int grid = (int)(tiles < n->n_sm ? tiles : n->n_sm);
+  static int dbg = -1;
+  if (dbg < 0) {
+    const char* e = getenv("SURF_T2_DEBUG");
+    dbg = e ? atoi(e) : 0;
+  }
+  const int flags = (negate ? 1 : 0) | (surf_mlp_mode() == 4 ? 2 : 0) | dbg;
+  surf_time_begin(d_grad ? 0 : 1, st);
+  if (d_grad) {
+    k_sdf_tc2<true><<<grid, T2_THREADS, S2_TOTAL + T2_TRACE_SMEM, st>>>(s->dev, n->dev, src, n->tc1_blob, stream, d_sdf, d_grad,
+                                                                        (uint4*)n->tc1_scratch, flags);
+  } else {
+    k_sdf_tc2<false><<<grid, T2_THREADS, S2_TOTAL + T2_TRACE_SMEM, st>>>(s->dev, n->dev, src, n->tc1_blob, stream, d_sdf, nullptr,
+                                                                         (uint4*)n->tc1_scratch, flags);
+  }
+  surf_time_end(d_grad ? 0 : 1, st);
+  SURF_LAUNCH_CHECK();
+  return 0;
+}
+
+#ifdef TC_TRACE
+extern "C" int surf_t2_trace_read(long long* h_out, int max_events) {
+  int n = 0;
+  cudaMemcpyFromSymbol(&n, g_t2_trace_n, sizeof(int));
+  if (n > max_events) n = max_events;
+  if (n > 4096) n = 4096;
+  cudaMemcpyFromSymbol(h_out, g_t2_trace, sizeof(long long) * 2 * n);
+  int zero = 0;
+  cudaMemcpyToSymbol(g_t2_trace_n, &zero, sizeof(int));
+  return n;
+}
+#endif

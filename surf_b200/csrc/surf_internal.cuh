@@ -282,6 +282,16 @@ int launch_sdf_mlp(const surf_scene* s, const surf_net* n, const PointSource& sr
                    bool negate, cudaStream_t st);
 int launch_sdf_tc_fwd(const surf_scene* s, const surf_net* n, const PointSource& src, float* d_sdf, bool negate,
                       cudaStream_t st);
+// weight stream of the tensor-core forward + reverse kernels (sdf_tc1.cu builds it, sdf_tc2.cu re-orders it)
+#define T1_MAXCHUNK 64
+struct T1Stream {
+  int n_fwd, n_all;
+  uint32_t off[T1_MAXCHUNK];      // byte offset in the blob
+  uint32_t bytes[T1_MAXCHUNK];
+};
+extern T1Stream g_t1_stream;
+int launch_sdf_tc2(const surf_scene* s, const surf_net* n, const PointSource& src, float* d_sdf, float* d_grad,
+                   bool negate, cudaStream_t st);
 int launch_sdf_tc1(const surf_scene* s, const surf_net* n, const PointSource& src, float* d_sdf, float* d_grad,
                    bool negate, cudaStream_t st);
 int launch_blend_tc(const surf_net* n, const float* d_feat, const float* d_raydiff, const uint8_t* d_mask, int V,

@@ -41,10 +41,11 @@ from surf_b200 import conf  # noqa: E402
 from surf_b200.modules.implicit_surface import ImplicitSurface  # noqa: E402
 
 
-@pytest.fixture
-def tc_mode():
-    _lib.set_mlp_mode(1)
-    yield
+# mode 1: the shipped tensor-core kernels; mode 5: the pipelined one-tile kernel (sdf_tc2.cu) for forward and gradient
+@pytest.fixture(params=[1, 5])
+def tc_mode(request):
+    _lib.set_mlp_mode(request.param)
+    yield request.param
     _lib.set_mlp_mode(0)
 
 
@@ -61,7 +62,7 @@ def test_tc_sdf_forward_vs_reference(name, tc_mode):
     assert_close(sdf_tc, g["out"]["_sdf_full"][:, :1], RTOL_FP32, "tensor-core sdf vs reference golden")
     _lib.set_mlp_mode(0)
     sdf_ffma = m.sdf_network.sdf(pv, ps)
-    _lib.set_mlp_mode(1)
+    _lib.set_mlp_mode(tc_mode)
     assert float((sdf_tc - sdf_ffma).abs().max()) < 2e-5
     for n in (1, 127, 128, 129, 255, 257, 1000):
         assert torch.equal(m.sdf_network.sdf(pv[:n], ps), sdf_tc[:n])

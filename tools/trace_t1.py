@@ -5,7 +5,7 @@ sys.path.insert(0, ROOT)
 import torch
 from surf_b200 import _lib, synthetic
 import bench
-_lib.set_mlp_mode(1)
+_lib.set_mlp_mode(int(os.environ.get('MLP_MODE', '1')))
 sc = synthetic.make_scene(3, 576, 800, 88, seed=1, device="cuda")
 m = bench.build_net("cuda")
 ps = m.prepare(sc.matching_volume, sc.volumes, sc.sparse_idxes, sc.mask_volumes, sc.imgs, sc.features, sc.intrs, sc.c2ws)
@@ -20,11 +20,12 @@ for _ in range(2):
     run()
 torch.cuda.synchronize()
 buf = (C.c_longlong * 8192)()
-lib.surf_t1_trace_read.restype = C.c_int
-lib.surf_t1_trace_read(buf, 4096)
+reader = lib.surf_t2_trace_read if os.environ.get("MLP_MODE") == "5" else lib.surf_t1_trace_read
+reader.restype = C.c_int
+reader(buf, 4096)
 run()
 torch.cuda.synchronize()
-n = lib.surf_t1_trace_read(buf, 4096)
+n = reader(buf, 4096)
 ev = sorted((buf[2 * i + 1], buf[2 * i]) for i in range(n))
 t0 = ev[0][0]
 def name(e):
@@ -36,8 +37,15 @@ def name(e):
     if 36 <= e < 42: return "epi  done  bwd L%d" % (5 - (e - 36))
     if 50 <= e < 70: return "iss  start  phase %d" % (e - 50)
     if 70 <= e < 90: return "iss  issued phase %d" % (e - 70)
+    if 1000 <= e < 2000: return "iss   wait w_full  p%d c%d" % ((e - 1000) // 8, (e - 1000) % 8)
+    if 2000 <= e < 3000: return "iss   got  w_full  p%d c%d" % ((e - 2000) // 8, (e - 2000) % 8)
+    if 6000 <= e < 7000:
+        k = e - 6000
+        return "epi    p%d g%d %s" % (k // 16, (k % 16) // 4, ("loaded", "computed", "signalled")[k % 4])
+    if 4000 <= e < 5000: return "iss   feat chunk issued p%d h%d" % ((e - 4000) // 8, (e - 4000) % 8)
+    if 3000 <= e < 4000: return "iss   committed    p%d c%d" % ((e - 3000) // 8, (e - 3000) % 8)
     return str(e)
 prev = t0
-for t, e in ev[:140]:
-    print("%9d (+%5d)  %s" % (t - t0, t - prev, name(e)))
+for t, e in ev[:1500]:
+    print("%9d (+%5d)  [%s] %s" % (t - t0, t - prev, ("w0 ", "iss", "w15")[e // 100000], name(e % 100000)))
     prev = t
