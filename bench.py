@@ -50,7 +50,7 @@ def parse():
     ap.add_argument("--cpu-rays", type=int, default=8192, help="rays per CPU-baseline sample / reference-arm step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
-    ap.add_argument("--mlp-mode", type=int, default=1, choices=[0, 1, 3, 4, 5],
+    ap.add_argument("--mlp-mode", type=int, default=1, choices=[0, 1, 3, 4],
                     help="0 = fp32 FFMA MLP kernels, 1 = tcgen05 kernels with the fp16 hi/lo 3-MMA split (fp32-grade), "
                          "4 = tcgen05 single fp16 MMA (opt-in 1e-2 mode)")
     return ap.parse_args()
@@ -361,7 +361,7 @@ def run_gpu(args):
         except Exception:
             traffic = None
     tc = args.mlp_mode >= 1
-    kname = ("k_sdf_tc1<GRAD=true> (tcgen05: sparse gather + SDF MLP forward + input gradient, fp16 hi/lo 3-MMA)" if tc
+    kname = ("k_sdf_tc2<GRAD=true> (tcgen05: sparse gather + SDF MLP forward + input gradient, fp16 hi/lo 3-MMA)" if tc
              else "k_sdf_mlp<GRAD=true> (fp32 FFMA: sparse gather + SDF MLP forward + input gradient)")
     roofline = {"kernel": kname, "bound": "tensor",
                 "achieved": achieved_tflops, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",

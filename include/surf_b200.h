@@ -120,7 +120,7 @@ typedef struct surf_render_cfg {
   const float* d_lin_tables;               /* torch.linspace(0,1,n) for n = n_samples[0..], then n_depth,
                                               concatenated (host-generated: linspace is not reproducible by
                                               a device formula) */
-  int32_t mlp_mode;                        /* 0 = fp32 FFMA, 1 = tensor-core (reserved) */
+  int32_t mlp_mode;                        /* reserved, ignored: the kernel family is process-wide, surf_set_mlp_mode */
 } surf_render_cfg;
 
 /* Outputs of render_core; any pointer may be NULL (not written).  Shapes use B rays, S samples,
@@ -212,11 +212,15 @@ int64_t surf_launch_count(void);
 int surf_timing_enable(int32_t on);
 int surf_timing_read(double* ms_out /*[SURF_TIMING_KINDS]*/, int64_t* launches_out /*[SURF_TIMING_KINDS]*/);
 
-/* Process-wide choice of the SDF-MLP kernel family: 0 = fp32 FFMA (default), 1 = tcgen05 tensor cores with the
- * fp16 hi/lo 3-MMA split (fp32-grade accuracy, bitwise reproducible), 2 = same with two MMA-issuing threads per
- * tile (experimental; the fp32 accumulation order then depends on timing), 3 = tcgen05 with the one-tile kernel
- * (sdf_tc1.cu) for the forward-only queries too (the gradient path always uses it in modes >= 1).
- * Kernels without a tensor-core edition keep using mode 0. */
+/* Process-wide choice of the SDF-MLP / blending kernel family:
+ *   0 = fp32 FFMA (default);
+ *   1 = tcgen05 tensor cores with the fp16 hi/lo 3-MMA split (fp32-grade accuracy, bitwise reproducible): the
+ *       pipelined one-tile kernel of sdf_tc2.cu for forward-only and forward + gradient queries, blend_tc.cu;
+ *   3 = the first-generation tensor-core kernels (sdf_tc.cu forward, sdf_tc1.cu forward + gradient), kept for
+ *       comparison; 2 = mode 3 with two MMA-issuing threads per tile in the forward kernel (experimental: the fp32
+ *       accumulation order then depends on timing);
+ *   4 = mode 1 with ONE fp16 MMA per product (opt-in reduced precision, 1e-2 relative).
+ * Kernels without a tensor-core edition keep using mode 0.  surf_render_cfg.mlp_mode is not consulted. */
 int surf_set_mlp_mode(int32_t mode);
 
 /* Diagnostic: one 128 x N x K GEMM through the tcgen05 building blocks of the tensor-core MLP kernels

@@ -212,5 +212,6 @@ def timing_read():
 
 
 def set_mlp_mode(mode: int):
-    """0 = fp32 FFMA kernels, 1 = tcgen05 tensor-core kernels (fp16 hi/lo split, fp32-grade accuracy)."""
+    """0 = fp32 FFMA kernels, 1 = tcgen05 tensor-core kernels (fp16 hi/lo split, fp32-grade accuracy),
+    3 = first-generation tensor-core kernels (comparison), 4 = single-MMA reduced precision (see include/surf_b200.h)."""
     check(load().surf_set_mlp_mode(int(mode)), "set_mlp_mode")

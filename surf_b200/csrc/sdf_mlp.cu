@@ -445,7 +445,7 @@ int surf_build_tc1_weights(const std::vector<std::vector<float>>& W, const surf_
 static int g_mlp_mode = 0;
 int surf_mlp_mode() { return g_mlp_mode; }
 extern "C" int surf_set_mlp_mode(int32_t mode) {
-  SURF_CHECK_ARG(mode >= 0 && mode <= 5, "mlp mode must be 0..5");
+  SURF_CHECK_ARG(mode >= 0 && mode <= 4, "mlp mode must be 0..4");
   g_mlp_mode = mode;
   return 0;
 }
@@ -587,9 +587,13 @@ int launch_sdf_mlp(const surf_scene* s, const surf_net* n, const PointSource& sr
   }
   if (src.n <= 0) return 0;
   if (g_mlp_mode >= 1 && n->tc_ok) {
-    if (g_mlp_mode == 5) return launch_sdf_tc2(s, n, src, d_sdf, d_grad, negate, st);
-    if (d_grad || g_mlp_mode == 3) return launch_sdf_tc1(s, n, src, d_sdf, d_grad, negate, st);
-    return launch_sdf_tc_fwd(s, n, src, d_sdf, negate, st);
+    // modes 1 / 4: the pipelined one-tile kernel (sdf_tc2.cu); modes 2 / 3: the first-generation kernels, kept for
+    // comparison (sdf_tc.cu: two forward tile pipelines; sdf_tc1.cu: forward + gradient, layer-serial)
+    if (g_mlp_mode == 2 || g_mlp_mode == 3) {
+      if (d_grad) return launch_sdf_tc1(s, n, src, d_sdf, d_grad, negate, st);
+      return launch_sdf_tc_fwd(s, n, src, d_sdf, negate, st);
+    }
+    return launch_sdf_tc2(s, n, src, d_sdf, d_grad, negate, st);
   }
   int64_t tiles = (src.n + MLP_TILE - 1) / MLP_TILE;
   int grid = (int)(tiles < n->n_sm ? tiles : n->n_sm);

@@ -12,6 +12,10 @@
 //     of the next A operand (fp16 hi [320,384) / lo [384,448)) is in TMEM;
 //   * K chunk g of layer p+1 (K = 32 = exactly those columns) is issued as soon as a_grp[g] fires; the feature /
 //     bias chunks of a forward layer do not depend on the previous layer at all and go first.
+//   * two helper warps own everything that touches global memory per point: they gather the sparse features and
+//     encode the positional encoding of tile t+1 into the second half of a double-buffered smem A operand while the
+//     16 epilogue warps run the layers of tile t, and afterwards turn tile t's feature / PE gradients into
+//     d sdf / d x (second gather, weights' derivative) — the epilogue warps never wait on a dependent global load.
 // One thread issues every MMA, in a fixed order, into one accumulator per layer: results are bitwise deterministic.
 // Weight stream, hi/lo fp16 split (3 MMAs per product), u-code scratch for softplus': as sdf_tc1.cu.
 #include <math.h>
@@ -23,9 +27,10 @@
 
 #define T2_EPI_WARPS 16
 #define T2_EPI_THREADS (T2_EPI_WARPS * 32)
-#define T2_THREADS ((T2_EPI_WARPS + 2) * 32)     // + 1 MMA issuer + 1 weight loader
+#define T2_HELP_WARPS 4
+#define T2_THREADS ((T2_EPI_WARPS + 2 + T2_HELP_WARPS) * 32)     // + 1 MMA issuer + 1 weight loader + helpers
 #define T2_SLOT_BYTES 20480                      // N = 160 x K = 32 x (hi + lo)
-#define T2_NSLOT 7
+#define T2_NSLOT 5
 
 #define T2_D0 0u
 #define T2_D1 160u
@@ -34,12 +39,13 @@
 
 // dynamic smem (bytes)
 #define S2_RING 0
-#define S2_AFEAT (S2_RING + T2_NSLOT * T2_SLOT_BYTES)      // hi 8 KB | lo 8 KB  (128 rows x K 32)
-#define S2_APE (S2_AFEAT + 16384)
-#define S2_W6 (S2_APE + 16384)                             // 160 floats
+#define S2_AFEAT (S2_RING + T2_NSLOT * T2_SLOT_BYTES)      // 2 buffers x (hi 8 KB | lo 8 KB)  (128 rows x K 32)
+#define S2_APE (S2_AFEAT + 2 * 16384)                      // 2 buffers
+#define S2_W6 (S2_APE + 2 * 16384)                         // 160 floats
 #define S2_PART (S2_W6 + 640)                              // [4][128] floats
-#define S2_GPE (S2_PART + 2048)                            // [28][128] floats
-#define S2_GF (S2_GPE + 14336)                             // [28][128] floats ; later [4][3][128] partial grads
+#define S2_GPE (S2_PART + 2048)                            // [28][128] floats: PE gradient through the skip layer
+#define S2_GPE0 (S2_GPE + 14336)                           // [28][128] floats: PE gradient through lin0
+#define S2_GF (S2_GPE0 + 14336)                            // [28][128] floats: feature gradient
 #define S2_BAR (S2_GF + 14336)
 #define S2_TOTAL (S2_BAR + 256)
 
@@ -48,11 +54,11 @@
 // issuer lane 0 -> slot 1, epilogue warp 15 lane 0 -> slot 2
 __device__ long long g_t2_trace[8192];
 __device__ int g_t2_trace_n;
-#define T2_TRACE_SMEM 24576
+#define T2_TRACE_SMEM 18432
 #define TRACE2(ev)                                                                  \
   do {                                                                              \
-    if (blockIdx.x == 0 && lane == 0 && trace_slot >= 0 && trace_n < 512) {        \
-      long long* _t = reinterpret_cast<long long*>(smem + S2_TOTAL) + trace_slot * 1024; \
+    if (blockIdx.x == 0 && lane == 0 && trace_slot >= 0 && trace_n < 384) {        \
+      long long* _t = reinterpret_cast<long long*>(smem + S2_TOTAL) + trace_slot * 768; \
       _t[2 * trace_n] = (ev);                                                       \
       _t[2 * trace_n + 1] = clock64();                                              \
       trace_n++;                                                                    \
@@ -67,8 +73,10 @@ struct T2Bars {
   uint64_t w_full[T2_NSLOT];
   uint64_t w_empty[T2_NSLOT];
   uint64_t d_full;          // all MMAs of a layer phase done (tcgen05.commit of the issuer)
-  uint64_t stage_ready;     // a tile's smem operands (features, PE) staged: one arrival per epilogue warp
+  uint64_t stage_ready[2];  // smem operands (features, PE) of a tile staged in buffer b: one arrival per helper warp
   uint64_t a_grp[4];        // column group g of the next A operand written: one arrival per epilogue warp
+  uint64_t grads_ready;     // a tile is through its layers (feature / PE gradients in smem): one arrival per epilogue warp
+  uint64_t finish_done;     // the helpers are done with a tile's gradients in smem: one arrival per helper warp
   uint32_t tmem_base;
 };
 
@@ -325,8 +333,11 @@ k_sdf_tc2(const DevScene sc, const DevNet net, const PointSource src, const uint
       tc::mbar_init(&bars->w_empty[i], 1);
     }
     tc::mbar_init(&bars->d_full, 1);
-    tc::mbar_init(&bars->stage_ready, T2_EPI_WARPS);
+    tc::mbar_init(&bars->stage_ready[0], T2_HELP_WARPS);
+    tc::mbar_init(&bars->stage_ready[1], T2_HELP_WARPS);
     for (int g = 0; g < 4; ++g) tc::mbar_init(&bars->a_grp[g], T2_EPI_WARPS);
+    tc::mbar_init(&bars->grads_ready, T2_EPI_WARPS);
+    tc::mbar_init(&bars->finish_done, T2_HELP_WARPS);
     tc::mbar_fence_init();
   }
   for (int i = tid; i < 160; i += T2_THREADS) sw6[i] = net.w6[i];
@@ -335,106 +346,58 @@ k_sdf_tc2(const DevScene sc, const DevNet net, const PointSource src, const uint
   tc::tc_fence_after();
   const uint32_t tbase = bars->tmem_base;
 
+  auto load_point = [&](int64_t i, float& px, float& py, float& pz) -> int64_t {
+    px = 0.f; py = 0.f; pz = 0.f;
+    if (i >= n_total) return -1;
+    const int64_t id = src.list ? (int64_t)src.list[i] : i;
+    if (src.mode == 0) {
+      px = src.pts[id * 3]; py = src.pts[id * 3 + 1]; pz = src.pts[id * 3 + 2];
+    } else if (src.mode == 1) {
+      const int64_t ray = id / src.S;
+      const float t = src.mid_z[id];
+      px = ray_at(src.rays_o[ray * 3], src.rays_d[ray * 3], t);
+      py = ray_at(src.rays_o[ray * 3 + 1], src.rays_d[ray * 3 + 1], t);
+      pz = ray_at(src.rays_o[ray * 3 + 2], src.rays_d[ray * 3 + 2], t);
+    } else {
+      const int64_t yz = (int64_t)src.ny * src.nz;
+      const int xi = (int)(id / yz);
+      const int rem = (int)(id - (int64_t)xi * yz);
+      px = src.xs[xi]; py = src.ys[rem / src.nz]; pz = src.zs[rem % src.nz];
+    }
+    return id;
+  };
+  float* s_gpe = reinterpret_cast<float*>(smem + S2_GPE);
+  float* s_gpe0 = reinterpret_cast<float*>(smem + S2_GPE0);
+  float* s_gf = reinterpret_cast<float*>(smem + S2_GF);
+
   if (warp < T2_EPI_WARPS) {
-    // =============================== epilogue / staging warps ===============================
+    // =============================== epilogue warps ===============================
     const int q = warp & 3, part = warp >> 2;
     const int r = q * 32 + lane;                 // row = point = TMEM lane
     const uint32_t tl = tbase + ((uint32_t)(q * 32) << 16);
-    uint8_t* afeat = smem + S2_AFEAT;
-    uint8_t* ape = smem + S2_APE;
     float* s_part = reinterpret_cast<float*>(smem + S2_PART);
-    float* s_gpe = reinterpret_cast<float*>(smem + S2_GPE);
-    float* s_gf = reinterpret_cast<float*>(smem + S2_GF);
     uint4* scratch = scratch_all + (size_t)blockIdx.x * (5 * 4 * T2_EPI_THREADS + 5 * T2_EPI_THREADS / 4);
     uint32_t* sgn_scratch = reinterpret_cast<uint32_t*>(scratch + 5 * 4 * T2_EPI_THREADS);
     const int te = warp * 32 + lane;             // 0..511
     uint32_t ph_d = 0;
-    auto put_k = [&](uint8_t* base, int k, float v) {
-      const __half h = __float2half_rn(v);
-      const __half l = __float2half_rn(v - __half2float(h));
-      const uint32_t off = (uint32_t)(k >> 3) * 2048u + r * 16 + (k & 7) * 2;
-      *reinterpret_cast<__half*>(base + off) = h;
-      *reinterpret_cast<__half*>(base + 8192 + off) = l;
-    };
-    auto get_k = [&](const uint8_t* base, int k) { return t2_get_k(base, r, k); };
     auto epi_bar = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(T2_EPI_THREADS) : "memory"); };
-    auto load_point = [&](int64_t i, float& px, float& py, float& pz) -> int64_t {
-      px = 0.f; py = 0.f; pz = 0.f;
-      if (i >= n_total) return -1;
-      const int64_t id = src.list ? (int64_t)src.list[i] : i;
-      if (src.mode == 0) {
-        px = src.pts[id * 3]; py = src.pts[id * 3 + 1]; pz = src.pts[id * 3 + 2];
-      } else if (src.mode == 1) {
-        const int64_t ray = id / src.S;
-        const float t = src.mid_z[id];
-        px = ray_at(src.rays_o[ray * 3], src.rays_d[ray * 3], t);
-        py = ray_at(src.rays_o[ray * 3 + 1], src.rays_d[ray * 3 + 1], t);
-        pz = ray_at(src.rays_o[ray * 3 + 2], src.rays_d[ray * 3 + 2], t);
-      } else {
-        const int64_t yz = (int64_t)src.ny * src.nz;
-        const int xi = (int)(id / yz);
-        const int rem = (int)(id - (int64_t)xi * yz);
-        px = src.xs[xi]; py = src.ys[rem / src.nz]; pz = src.zs[rem % src.nz];
-      }
-      return id;
-    };
 
     T2Epi ec;
-    ec.tl = tl; ec.part = part; ec.r = r; ec.te = te; ec.ape = ape; ec.sw6 = sw6; ec.inv_scale = net.inv_scale;
+    ec.tl = tl; ec.part = part; ec.r = r; ec.te = te; ec.ape = nullptr; ec.sw6 = sw6; ec.inv_scale = net.inv_scale;
     ec.scratch = scratch; ec.sgn_scratch = sgn_scratch; ec.s_gpe = s_gpe; ec.dbg = flags;
 
-    float nf7[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // next tile's features of (row, level = part), gathered early
-    bool have_next = false;
     for (int64_t it = 0; it < my_tiles; ++it) {
       const int64_t tile = (int64_t)blockIdx.x + it * gridDim.x;
-      float px, py, pz;
-      const int64_t id = load_point(tile * 128 + r, px, py, pz);
-      // ---- staging: thread (row, part) gathers level `part` and encodes PE frequency `part` ----
-      {
-        float f7[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        if (GRAD && have_next) {
-#pragma unroll
-          for (int c = 0; c < 7; ++c) f7[c] = nf7[c];
-        } else if (part < sc.n_levels && !(flags & 64)) {
-          sparse_level<0>(sc, part, px, py, pz, nullptr, f7);
-        }
-#pragma unroll
-        for (int c = 0; c < 7; ++c) put_k(afeat, part * 7 + c, f7[c]);
-        const float xs[3] = {px * net.scale, py * net.scale, pz * net.scale};
-        if (part == 0) {
-#pragma unroll
-          for (int d = 0; d < 3; ++d) put_k(ape, d, xs[d]);
-        }
-        if (part == 3) {
-          put_k(afeat, 28, 1.0f);
-          put_k(ape, 27, 1.0f);
-#pragma unroll
-          for (int k = 29; k < 32; ++k) put_k(afeat, k, 0.f);
-#pragma unroll
-          for (int k = 28; k < 32; ++k) put_k(ape, k, 0.f);
-        }
-        const float fr = (float)(1 << part);
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-          float sn = 0.f, cs = 0.f;
-          if (part < net.multires) sincosf(xs[d] * fr, &sn, &cs);
-          put_k(ape, 3 + 6 * part + d, sn);
-          put_k(ape, 3 + 6 * part + 3 + d, cs);
-        }
-      }
-      tc::fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&bars->stage_ready);
+      const int buf = (int)(it & 1);
+      const uint8_t* afeat = smem + S2_AFEAT + buf * 16384;
+      ec.ape = smem + S2_APE + buf * 16384;
+      // the helpers staged this tile a whole tile ago; the wait is the acquire for my reads of their smem writes
+      tc::mbar_wait(&bars->stage_ready[buf], (uint32_t)((it >> 1) & 1));
       if (warp == 0) TRACE2(1);
 
       float gf[8];          // reverse pass: d sdf / d feat for feature columns part*8 .. part*8+7
       // ------------------------------------ forward ------------------------------------
       for (int l = 0; l < 6; ++l) {
-        if (l == 1 && it + 1 < my_tiles && part < sc.n_levels) {
-          // while the tensor core works on this layer: pull the NEXT tile's gather working set into L2
-          float nx, ny, nz;
-          if (load_point((tile + gridDim.x) * 128 + r, nx, ny, nz) >= 0 && !(flags & 64)) sparse_prefetch_l2(sc, part, nx, ny, nz);
-        }
         tc::mbar_wait(&bars->d_full, ph_d & 1);
         ph_d++;
         tc::tc_fence_after();
@@ -449,35 +412,28 @@ k_sdf_tc2(const DevScene sc, const DevNet net, const PointSource src, const uint
           if (part == 0) {
             float s = s_part[r] + s_part[128 + r] + s_part[256 + r] + s_part[384 + r] + net.b6;
 #pragma unroll
-            for (int c = 0; c < 28; ++c) s = fmaf(get_k(afeat, c), sw6[128 + c], s);
+            for (int c = 0; c < 28; ++c) s = fmaf(t2_get_k(afeat, r, c), sw6[128 + c], s);
             s *= net.inv_scale;
-            if (id >= 0) sdf_out[id] = (flags & 1) ? -s : s;
-          }
-          if (!GRAD) {
-            tc::tc_fence_before();
-            epi_bar();            // afeat / s_part reads done before the next tile restages
+            const int64_t i = tile * 128 + r;
+            if (i < n_total) {
+              const int64_t id = src.list ? (int64_t)src.list[i] : i;
+              sdf_out[id] = (flags & 1) ? -s : s;
+            }
           }
         }
       }
-      if (!GRAD) continue;
+      if (!GRAD) {
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&bars->grads_ready);       // this tile's smem operands may be restaged
+        continue;
+      }
 
       // ------------------------------------ reverse ------------------------------------
+      // the helpers must be done reading the previous tile's gradients before this tile's overwrite them
+      if (it > 0) tc::mbar_wait(&bars->finish_done, (uint32_t)((it - 1) & 1));
 #pragma unroll
       for (int j = 0; j < 8; ++j) gf[j] = sw6[128 + part * 8 + j] * net.inv_scale;
       for (int l = 5; l >= 1; --l) {
-        if (l == 4) {
-          // gather the NEXT tile's features now (its lines were prefetched into L2 during lin1): the load latency
-          // hides behind this layer's MMAs and the next tile's staging shrinks to the smem writes
-          have_next = false;
-          if (it + 1 < my_tiles) {
-            float nx, ny, nz;
-            load_point((tile + gridDim.x) * 128 + r, nx, ny, nz);
-#pragma unroll
-            for (int c = 0; c < 7; ++c) nf7[c] = 0.f;
-            if (part < sc.n_levels && !(flags & 64)) sparse_level<0>(sc, part, nx, ny, nz, nullptr, nf7);
-            have_next = true;
-          }
-        }
         tc::mbar_wait(&bars->d_full, ph_d & 1);
         ph_d++;
         tc::tc_fence_after();
@@ -489,17 +445,7 @@ k_sdf_tc2(const DevScene sc, const DevNet net, const PointSource src, const uint
 #pragma unroll
       for (int j = 0; j < 8; ++j)
         if (part * 8 + j < 28) s_gf[(part * 8 + j) * 128 + r] = gf[j];
-      epi_bar();                                   // s_gpe (skip part) and s_gf complete
-      // d feats / d x for level `part` (re-gather; lines were touched a tile ago, L2 hits) — issued before
-      // waiting for the lin0 reverse MMAs so its latency overlaps them
-      float o3[3] = {0.f, 0.f, 0.f};
-      if (part < sc.n_levels && !(flags & 64)) {
-        float g7[7];
-#pragma unroll
-        for (int c = 0; c < 7; ++c) g7[c] = s_gf[(part * 7 + c) * 128 + r];
-        sparse_level<1>(sc, part, px, py, pz, g7, o3);
-      }
-      // ---- reverse of lin0: g_pe += delta0 . W0 (N = 32), phase 11 -> D1 ----
+      // ---- reverse of lin0: PE gradient through lin0 = delta0 . W0 (N = 32), phase 11 -> D1 ----
       tc::mbar_wait(&bars->d_full, ph_d & 1);
       ph_d++;
       tc::tc_fence_after();
@@ -512,32 +458,13 @@ k_sdf_tc2(const DevScene sc, const DevNet net, const PointSource src, const uint
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int k = hb * 16 + j;
-            if (k < 27) s_gpe[k * 128 + r] += __uint_as_float(a[j]);
+            if (k < 27) s_gpe0[k * 128 + r] = __uint_as_float(a[j]);
           }
         }
       }
       tc::tc_fence_before();
-      epi_bar();                                   // all s_gf reads done, s_gpe final
-      float* s_pg = s_gf;                          // reuse as [4][3][128]
-      s_pg[(part * 3 + 0) * 128 + r] = o3[0];
-      s_pg[(part * 3 + 1) * 128 + r] = o3[1];
-      s_pg[(part * 3 + 2) * 128 + r] = o3[2];
-      epi_bar();
-      if (part < 3 && id >= 0) {                   // thread (row, d = part) finishes component d
-        const int d = part;
-        float gx = s_gpe[d * 128 + r];
-        float fr = 1.0f;
-        for (int f = 0; f < net.multires; ++f) {
-          const float sn = get_k(ape, 3 + 6 * f + d), cs = get_k(ape, 3 + 6 * f + 3 + d);
-          gx += fr * (s_gpe[(3 + 6 * f + d) * 128 + r] * cs - s_gpe[(3 + 6 * f + 3 + d) * 128 + r] * sn);
-          fr *= 2.0f;
-        }
-        gx *= net.scale;
-#pragma unroll
-        for (int lv = 0; lv < 4; ++lv) gx += s_pg[(lv * 3 + d) * 128 + r];
-        grad_out[id * 3 + d] = gx;
-      }
-      epi_bar();                                   // smem scratch free for the next tile
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&bars->grads_ready);         // the helpers turn s_gf / s_gpe / s_gpe0 into d sdf / d x
       if (warp == 0) TRACE2(99);
     }
   } else if (warp == T2_EPI_WARPS) {
@@ -551,10 +478,10 @@ k_sdf_tc2(const DevScene sc, const DevNet net, const PointSource src, const uint
       // descriptor constant parts: SBO 128; LBO = rows * 16
       const uint64_t d128 = tc::smem_desc_kmajor(0, 2048, 128), d160 = tc::smem_desc_kmajor(0, 2560, 128),
                      d32 = tc::smem_desc_kmajor(0, 512, 128);
-      const uint32_t afeat_lo = (uint32_t)d128 | (tc::smem_u32(smem + S2_AFEAT) >> 4);
-      const uint32_t ape_lo = (uint32_t)d128 | (tc::smem_u32(smem + S2_APE) >> 4);
+      const uint32_t afeat_lo0 = (uint32_t)d128 | (tc::smem_u32(smem + S2_AFEAT) >> 4);
+      const uint32_t ape_lo0 = (uint32_t)d128 | (tc::smem_u32(smem + S2_APE) >> 4);
       const uint32_t dh128 = (uint32_t)(d128 >> 32), dh160 = (uint32_t)(d160 >> 32), dh32 = (uint32_t)(d32 >> 32);
-      uint32_t ph_stage = 0, ph_grp = 0;
+      uint32_t ph_grp = 0;
       int slot = 0;
       uint32_t ring_par = 0;
       // wait for the next weight chunk; returns its smem address in 16-byte units
@@ -569,19 +496,26 @@ k_sdf_tc2(const DevScene sc, const DevNet net, const PointSource src, const uint
       };
       for (int64_t it = 0; it < my_tiles; ++it) {
         // ---- phase 0: lin0 on the positional encoding (A in smem) -> D0 ----
-        tc::mbar_wait(&bars->stage_ready, ph_stage & 1);
-        ph_stage++;
+        const int buf = (int)(it & 1);
+        const uint32_t afeat_lo = afeat_lo0 + buf * 1024, ape_lo = ape_lo0 + buf * 1024;     // 16384 B in 16-byte units
+        tc::mbar_wait(&bars->stage_ready[buf], (uint32_t)((it >> 1) & 1));
         tc::tc_fence_after();
         TRACE2(50);
         {
           const uint32_t tD = tbase + T2_D0;
           const uint32_t w0 = (uint32_t)d128 | next_chunk(), dh = dh128, a0 = ape_lo;
-          if (!nomma) tc::mma_ss_w<false>(tD, a0, dh, w0, dh, id128);
-          if (!nomma) if (!fast) tc::mma_ss_w<true>(tD, a0 + 512, dh, w0, dh, id128);
-          if (!nomma) if (!fast) tc::mma_ss_w<true>(tD, a0, dh, w0 + 512, dh, id128);
+          // the small correction products (lo x hi, hi x lo) go first: the tensor core's fp32 accumulation truncates,
+          // so they are added while the accumulator is still small
+          if (!nomma && !fast) {
+            tc::mma_ss_w<false>(tD, a0 + 512, dh, w0, dh, id128);
+            tc::mma_ss_w<true>(tD, a0, dh, w0 + 512, dh, id128);
+            tc::mma_ss_w<true>(tD, a0 + 768, dh, w0 + 256, dh, id128);
+            tc::mma_ss_w<true>(tD, a0 + 256, dh, w0 + 768, dh, id128);
+            tc::mma_ss_w<true>(tD, a0, dh, w0, dh, id128);
+          } else if (!nomma) {
+            tc::mma_ss_w<false>(tD, a0, dh, w0, dh, id128);
+          }
           if (!nomma) tc::mma_ss_w<true>(tD, a0 + 256, dh, w0 + 256, dh, id128);
-          if (!nomma) if (!fast) tc::mma_ss_w<true>(tD, a0 + 768, dh, w0 + 256, dh, id128);
-          if (!nomma) if (!fast) tc::mma_ss_w<true>(tD, a0 + 256, dh, w0 + 768, dh, id128);
           release_chunk();
           tc::mma_commit(&bars->d_full);
           TRACE2(70);
@@ -596,9 +530,13 @@ k_sdf_tc2(const DevScene sc, const DevNet net, const PointSource src, const uint
           for (int h = 0; h < 2; ++h) {
             const uint32_t w0 = (uint32_t)d128 | next_chunk();
             const uint32_t a0 = afeat_lo + h * 256;
-            if (!nomma) if (h == 0) tc::mma_ss_w<false>(tD, a0, dh, w0, dh, id128); else tc::mma_ss_w<true>(tD, a0, dh, w0, dh, id128);
-            if (!nomma) if (!fast) tc::mma_ss_w<true>(tD, a0 + 512, dh, w0, dh, id128);
-            if (!nomma) if (!fast) tc::mma_ss_w<true>(tD, a0, dh, w0 + 256, dh, id128);
+            if (!nomma && !fast) {
+              if (h == 0) tc::mma_ss_w<false>(tD, a0 + 512, dh, w0, dh, id128); else tc::mma_ss_w<true>(tD, a0 + 512, dh, w0, dh, id128);
+              tc::mma_ss_w<true>(tD, a0, dh, w0 + 256, dh, id128);
+              tc::mma_ss_w<true>(tD, a0, dh, w0, dh, id128);
+            } else if (!nomma) {
+              if (h == 0) tc::mma_ss_w<false>(tD, a0, dh, w0, dh, id128); else tc::mma_ss_w<true>(tD, a0, dh, w0, dh, id128);
+            }
             release_chunk();
             TRACE2(4000 + p * 8 + h);
           }
@@ -610,12 +548,14 @@ k_sdf_tc2(const DevScene sc, const DevNet net, const PointSource src, const uint
             TRACE2(2000 + p * 8 + c);
             const uint32_t w0 = (uint32_t)d128 | next_chunk();
             const uint32_t ah = tAhi + c * 16, al = tAlo + c * 16;
+            if (!nomma && !fast) {
+              tc::mma_ts_w<true>(tD, al, w0, dh, id128);
+              tc::mma_ts_w<true>(tD, ah, w0 + 512, dh, id128);
+              tc::mma_ts_w<true>(tD, al + 8, w0 + 256, dh, id128);
+              tc::mma_ts_w<true>(tD, ah + 8, w0 + 768, dh, id128);
+            }
             if (!nomma) tc::mma_ts_w<true>(tD, ah, w0, dh, id128);
-            if (!nomma) if (!fast) tc::mma_ts_w<true>(tD, al, w0, dh, id128);
-            if (!nomma) if (!fast) tc::mma_ts_w<true>(tD, ah, w0 + 512, dh, id128);
             if (!nomma) tc::mma_ts_w<true>(tD, ah + 8, w0 + 256, dh, id128);
-            if (!nomma) if (!fast) tc::mma_ts_w<true>(tD, al + 8, w0 + 256, dh, id128);
-            if (!nomma) if (!fast) tc::mma_ts_w<true>(tD, ah + 8, w0 + 768, dh, id128);
             release_chunk();
           }
           ph_grp++;
@@ -635,12 +575,16 @@ k_sdf_tc2(const DevScene sc, const DevNet net, const PointSource src, const uint
             TRACE2(2000 + p * 8 + c);
             const uint32_t w0 = (uint32_t)d160 | next_chunk();
             const uint32_t ah = tAhi + c * 16, al = tAlo + c * 16;
-            if (!nomma) if (c == 0) tc::mma_ts_w<false>(tD, ah, w0, dh, id160); else tc::mma_ts_w<true>(tD, ah, w0, dh, id160);
-            if (!nomma) if (!fast) tc::mma_ts_w<true>(tD, al, w0, dh, id160);
-            if (!nomma) if (!fast) tc::mma_ts_w<true>(tD, ah, w0 + 640, dh, id160);
+            if (!nomma && !fast) {
+              if (c == 0) tc::mma_ts_w<false>(tD, al, w0, dh, id160); else tc::mma_ts_w<true>(tD, al, w0, dh, id160);
+              tc::mma_ts_w<true>(tD, ah, w0 + 640, dh, id160);
+              tc::mma_ts_w<true>(tD, al + 8, w0 + 320, dh, id160);
+              tc::mma_ts_w<true>(tD, ah + 8, w0 + 960, dh, id160);
+              tc::mma_ts_w<true>(tD, ah, w0, dh, id160);
+            } else if (!nomma) {
+              if (c == 0) tc::mma_ts_w<false>(tD, ah, w0, dh, id160); else tc::mma_ts_w<true>(tD, ah, w0, dh, id160);
+            }
             if (!nomma) tc::mma_ts_w<true>(tD, ah + 8, w0 + 320, dh, id160);
-            if (!nomma) if (!fast) tc::mma_ts_w<true>(tD, al + 8, w0 + 320, dh, id160);
-            if (!nomma) if (!fast) tc::mma_ts_w<true>(tD, ah + 8, w0 + 960, dh, id160);
             release_chunk();
           }
           ph_grp++;
@@ -673,6 +617,103 @@ k_sdf_tc2(const DevScene sc, const DevNet net, const PointSource src, const uint
         }
       }
     }
+  } else if (warp >= T2_EPI_WARPS + 2) {
+    // =============================== helper warps: staging and the final gradient ===============================
+    const int hl = (warp - (T2_EPI_WARPS + 2)) * 32 + lane;       // 0..63: rows hl and hl + 64
+    auto put_k = [&](uint8_t* base, int r, int k, float v) {
+      const __half h = __float2half_rn(v);
+      const __half l = __float2half_rn(v - __half2float(h));
+      const uint32_t off = (uint32_t)(k >> 3) * 2048u + r * 16 + (k & 7) * 2;
+      *reinterpret_cast<__half*>(base + off) = h;
+      *reinterpret_cast<__half*>(base + 8192 + off) = l;
+    };
+    // features (4 levels x 7, trilinear) and positional encoding of tile `it` -> smem A operands of buffer it & 1
+    auto stage = [&](int64_t it) {
+      const int64_t tile = (int64_t)blockIdx.x + it * gridDim.x;
+      const int buf = (int)(it & 1);
+      uint8_t* afeat = smem + S2_AFEAT + buf * 16384;
+      uint8_t* ape = smem + S2_APE + buf * 16384;
+#pragma unroll 1
+      for (int h = 0; h < 128 / (T2_HELP_WARPS * 32); ++h) {
+        const int r = hl + h * (T2_HELP_WARPS * 32);
+        float px, py, pz;
+        load_point(tile * 128 + r, px, py, pz);
+#pragma unroll
+        for (int lv = 0; lv < 4; ++lv) {
+          float f7[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          if (lv < sc.n_levels && !(flags & 64)) sparse_level<0>(sc, lv, px, py, pz, nullptr, f7);
+#pragma unroll
+          for (int c = 0; c < 7; ++c) put_k(afeat, r, lv * 7 + c, f7[c]);
+        }
+        put_k(afeat, r, 28, 1.0f);
+#pragma unroll
+        for (int k = 29; k < 32; ++k) put_k(afeat, r, k, 0.f);
+        const float xs[3] = {px * net.scale, py * net.scale, pz * net.scale};
+#pragma unroll
+        for (int d = 0; d < 3; ++d) put_k(ape, r, d, xs[d]);
+        float fr = 1.0f;
+#pragma unroll
+        for (int f = 0; f < 4; ++f) {
+#pragma unroll
+          for (int d = 0; d < 3; ++d) {
+            float sn = 0.f, cs = 0.f;
+            if (f < net.multires) sincosf(xs[d] * fr, &sn, &cs);
+            put_k(ape, r, 3 + 6 * f + d, sn);
+            put_k(ape, r, 3 + 6 * f + 3 + d, cs);
+          }
+          fr *= 2.0f;
+        }
+        put_k(ape, r, 27, 1.0f);
+#pragma unroll
+        for (int k = 28; k < 32; ++k) put_k(ape, r, k, 0.f);
+      }
+      tc::fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&bars->stage_ready[buf]);
+    };
+    // d sdf / d x of tile `it` = scale * (d PE / d x)^T g_pe + sum over levels (d feat / d x)^T g_feat
+    auto finish = [&](int64_t it) {
+      const int64_t tile = (int64_t)blockIdx.x + it * gridDim.x;
+      const uint8_t* ape = smem + S2_APE + (it & 1) * 16384;
+#pragma unroll 1
+      for (int h = 0; h < 128 / (T2_HELP_WARPS * 32); ++h) {
+        const int r = hl + h * (T2_HELP_WARPS * 32);
+        float px, py, pz;
+        const int64_t id = load_point(tile * 128 + r, px, py, pz);
+        float acc[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for (int lv = 0; lv < 4; ++lv) {
+          if (lv < sc.n_levels && !(flags & 64)) {
+            float g7[7], o3[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+            for (int c = 0; c < 7; ++c) g7[c] = s_gf[(lv * 7 + c) * 128 + r];
+            sparse_level<1>(sc, lv, px, py, pz, g7, o3);
+            acc[0] += o3[0]; acc[1] += o3[1]; acc[2] += o3[2];
+          }
+        }
+        auto gpe = [&](int k) { return s_gpe[k * 128 + r] + s_gpe0[k * 128 + r]; };
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          float gx = gpe(d);
+          float fr = 1.0f;
+          for (int f = 0; f < net.multires; ++f) {
+            const float sn = t2_get_k(ape, r, 3 + 6 * f + d), cs = t2_get_k(ape, r, 3 + 6 * f + 3 + d);
+            gx += fr * (gpe(3 + 6 * f + d) * cs - gpe(3 + 6 * f + 3 + d) * sn);
+            fr *= 2.0f;
+          }
+          gx = fmaf(gx, net.scale, acc[d]);
+          if (id >= 0) grad_out[id * 3 + d] = gx;
+        }
+      }
+    };
+    if (my_tiles > 0) stage(0);
+    for (int64_t it = 0; it < my_tiles; ++it) {
+      if (it + 1 < my_tiles) stage(it + 1);       // buffer (it+1) & 1: tile it-1 released it in the previous round
+      tc::mbar_wait(&bars->grads_ready, (uint32_t)(it & 1));
+      if (GRAD) finish(it);
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&bars->finish_done);
+    }
   } else {
     // =============================== weight loader ===============================
     if (lane == 0) {
@@ -694,7 +735,7 @@ k_sdf_tc2(const DevScene sc, const DevNet net, const PointSource src, const uint
   }
 #ifdef TC_TRACE
   if (blockIdx.x == 0 && lane == 0 && trace_slot >= 0) {
-    const long long* _t = reinterpret_cast<const long long*>(smem + S2_TOTAL) + trace_slot * 1024;
+    const long long* _t = reinterpret_cast<const long long*>(smem + S2_TOTAL) + trace_slot * 768;
     const int base = atomicAdd(&g_t2_trace_n, trace_n);
     for (int i = 0; i < trace_n && base + i < 4096; ++i) {
       g_t2_trace[2 * (base + i)] = _t[2 * i] + 100000ll * trace_slot;

@@ -41,8 +41,8 @@ from surf_b200 import conf  # noqa: E402
 from surf_b200.modules.implicit_surface import ImplicitSurface  # noqa: E402
 
 
-# mode 1: the shipped tensor-core kernels; mode 5: the pipelined one-tile kernel (sdf_tc2.cu) for forward and gradient
-@pytest.fixture(params=[1, 5])
+# mode 1: the shipped tensor-core kernels (pipelined one-tile kernel, sdf_tc2.cu); mode 3: the first-generation ones
+@pytest.fixture(params=[1, 3])
 def tc_mode(request):
     _lib.set_mlp_mode(request.param)
     yield request.param
@@ -107,8 +107,6 @@ def test_tc_gradient_vs_reference(name, tc_mode):
     for n in (1, 127, 129, 300):
         s3, g3 = m.sdf_network.gradient(pv[:n], ps, with_sdf=True)
         assert torch.equal(s3, sdf[:n]) and torch.equal(g3, grad[:n])
-    _lib.set_mlp_mode(3)
-    assert_close(m.sdf_network.sdf(pv, ps), g["out"]["_sdf_full"][:, :1], RTOL_FP32, "tc1 forward-only sdf")
 
 
 def test_tc_gradient_wild_points(tc_mode):

@@ -20,7 +20,7 @@ for _ in range(2):
     run()
 torch.cuda.synchronize()
 buf = (C.c_longlong * 8192)()
-reader = lib.surf_t2_trace_read if os.environ.get("MLP_MODE") == "5" else lib.surf_t1_trace_read
+reader = lib.surf_t1_trace_read if os.environ.get("MLP_MODE") == "3" else lib.surf_t2_trace_read
 reader.restype = C.c_int
 reader(buf, 4096)
 run()
