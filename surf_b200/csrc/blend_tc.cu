@@ -262,7 +262,7 @@ k_blend_tc(const uint8_t* __restrict__ wtc, const float* __restrict__ wf32, floa
     }
     publish();
     // ---- base_fc.0 : 57(64) -> 64, ELU ----
-    if (tid == 0) bt_issue<64, 4>(tbase, aop_a, w_a + W_BASE0, &bars->mma_done, fast);
+    if (warp == 0 && tc::elect_one()) bt_issue<64, 4>(tbase, aop_a, w_a + W_BASE0, &bars->mma_done, fast);
     wait_mma();
     {
       uint32_t acc[32];
@@ -278,7 +278,7 @@ k_blend_tc(const uint8_t* __restrict__ wtc, const float* __restrict__ wf32, floa
     }
     publish();
     // ---- base_fc.2 : 64 -> 32, ELU -> x (fp32) ; next A operand = x * pooling weight ----
-    if (tid == 0) bt_issue<32, 4>(tbase, aop_a, w_a + W_BASE1, &bars->mma_done, fast);
+    if (warp == 0 && tc::elect_one()) bt_issue<32, 4>(tbase, aop_a, w_a + W_BASE1, &bars->mma_done, fast);
     wait_mma();
     {
       uint32_t acc[16];
@@ -296,7 +296,7 @@ k_blend_tc(const uint8_t* __restrict__ wtc, const float* __restrict__ wf32, floa
     }
     publish();
     // ---- vis_fc.0 : 32 -> 32, ELU ----
-    if (tid == 0) bt_issue<32, 2>(tbase, aop_a, w_a + W_VIS0, &bars->mma_done, fast);
+    if (warp == 0 && tc::elect_one()) bt_issue<32, 2>(tbase, aop_a, w_a + W_VIS0, &bars->mma_done, fast);
     wait_mma();
     {
       uint32_t acc[16];
@@ -309,7 +309,7 @@ k_blend_tc(const uint8_t* __restrict__ wtc, const float* __restrict__ wf32, floa
     }
     publish();
     // ---- vis_fc.2 : 32 -> 33, ELU ; x += x_res ; vis = sigmoid(.) * mask ----
-    if (tid == 0) bt_issue<48, 2>(tbase, aop_a, w_a + W_VIS1, &bars->mma_done, fast);
+    if (warp == 0 && tc::elect_one()) bt_issue<48, 2>(tbase, aop_a, w_a + W_VIS1, &bars->mma_done, fast);
     wait_mma();
     {
       uint32_t acc[16];
@@ -337,7 +337,7 @@ k_blend_tc(const uint8_t* __restrict__ wtc, const float* __restrict__ wf32, floa
     }
     publish();
     // ---- vis_fc2.0 : 32 -> 32, ELU ; vis_fc2.2 : 32 -> 1 (CUDA cores), sigmoid * mask ----
-    if (tid == 0) bt_issue<32, 2>(tbase, aop_a, w_a + W_V20, &bars->mma_done, fast);
+    if (warp == 0 && tc::elect_one()) bt_issue<32, 2>(tbase, aop_a, w_a + W_V20, &bars->mma_done, fast);
     wait_mma();
     {
       uint32_t acc[16];
@@ -368,7 +368,7 @@ k_blend_tc(const uint8_t* __restrict__ wtc, const float* __restrict__ wf32, floa
     }
     publish();
     // ---- rgb_fc.0 : 37(48) -> 16, ELU ; rgb_fc.2/.4 : 16 -> 8 -> 1 on the CUDA cores ----
-    if (tid == 0) bt_issue<16, 3>(tbase, aop_a, w_a + W_RGB0, &bars->mma_done, fast);
+    if (warp == 0 && tc::elect_one()) bt_issue<16, 3>(tbase, aop_a, w_a + W_RGB0, &bars->mma_done, fast);
     wait_mma();
     {
       float* A16 = F;                                   // [16][BS], feat buffer is free now

@@ -283,7 +283,7 @@ k_sdf_tc_fwd(const DevScene sc, const DevNet net, const PointSource src, const u
     const int sub = (warp - TC_EPI_WARPS) & 1;
     const bool fast = (two_issuers & 2) != 0;   // single fp16 MMA per product (opt-in reduced-precision mode)
     two_issuers &= 1;
-    if (lane == 0) {
+    if (tc::elect_one()) {
       const uint32_t idesc = tc::idesc_f16(128, 128, 0);
       const uint32_t ring = tc::smem_u32(smem + TS_RING);
       const uint32_t tD = tbase + g * 256, tAhi = tD + 128, tAlo = tD + 192;

@@ -501,7 +501,7 @@ k_sdf_tc1(const DevScene sc, const DevNet net, const PointSource src, const uint
     // =============================== MMA issuers: sub 0 -> D_a, sub 1 -> D_b ===============================
     const int sub = warp - T1_EPI_WARPS;
     const bool fast = (negate & 2) != 0;      // single fp16 MMA per product (opt-in reduced-precision mode)
-    if (lane == 0) {
+    if (tc::elect_one()) {
       const uint32_t ring = tc::smem_u32(smem + S1_RING);
       const uint32_t tD = tbase + (sub ? T1_DB : T1_DA);
       const uint32_t tAhi = tbase + T1_AHI, tAlo = tbase + T1_ALO;

@@ -68,6 +68,11 @@ __device__ int g_t2_trace_n;
 #define T2_TRACE_SMEM 0
 #define TRACE2(ev) do {} while (0)
 #endif
+#ifdef TC_TRACE_GROUPS            // per-group epilogue events (heavier: they slow the traced warps down)
+#define TRACE2G(ev) TRACE2(ev)
+#else
+#define TRACE2G(ev) do {} while (0)
+#endif
 
 struct T2Bars {
   uint64_t w_full[T2_NSLOT];
@@ -237,7 +242,7 @@ __device__ __forceinline__ void t2_fwd_layer(const T2Epi& c, T2Bars* bars, int l
 #pragma unroll
     for (int j = 0; j < 8; ++j) dv[j] = dn[j];
     if (g < 3) tc::tmem_ld8(dcol + (g + 1) * 32, dn);
-    TRACE2(6000 + l * 16 + g * 4);
+    TRACE2G(6000 + l * 16 + g * 4);
     const int cb = g * 32 + c.part * 8;
     uint4 spw = make_uint4(0u, 0u, 0u, 0u);
     float h[8];
@@ -250,10 +255,10 @@ __device__ __forceinline__ void t2_fwd_layer(const T2Epi& c, T2Bars* bars, int l
     } else {
       t2_fwd_act<GRAD, 0, HEAD>(c, cb, dv, h, spw, sgn, head);
     }
-    TRACE2(6000 + l * 16 + g * 4 + 1);
+    TRACE2G(6000 + l * 16 + g * 4 + 1);
     if (SIGNAL && g > 0) t2_signal_group(&bars->a_grp[g - 1], lane);
     if (SIGNAL) t2_store_a(c, cb, h);
-    TRACE2(6000 + l * 16 + g * 4 + 2);
+    TRACE2G(6000 + l * 16 + g * 4 + 2);
     if (GRAD && !HEAD && !(c.dbg & 16)) c.scratch[(size_t)(l * 4 + g) * T2_EPI_THREADS + c.te] = spw;
   }
   if (SIGNAL) t2_signal_group(&bars->a_grp[3], lane);
@@ -276,7 +281,7 @@ __device__ __forceinline__ void t2_bwd_layer(const T2Epi& c, T2Bars* bars, int p
 #pragma unroll
     for (int j = 0; j < 8; ++j) dv[j] = dn[j];
     tc::tmem_ld8(dbase + (g + 1) * 32, dn);               // g == 3: the feature-gradient columns 128 + part*8 ..
-    TRACE2(6000 + p * 16 + g * 4);
+    TRACE2G(6000 + p * 16 + g * 4);
     const uint4 spw_cur = spw;
     if (g < 3 && !(c.dbg & 16)) spw = c.scratch[(size_t)(lsrc * 4 + g + 1) * T2_EPI_THREADS + c.te];     // next group's codes
     const int cb = g * 32 + c.part * 8;
@@ -290,10 +295,10 @@ __device__ __forceinline__ void t2_bwd_layer(const T2Epi& c, T2Bars* bars, int p
     } else {
       t2_bwd_act<0>(c, cb, dv, spw_cur, sgn, v);
     }
-    TRACE2(6000 + p * 16 + g * 4 + 1);
+    TRACE2G(6000 + p * 16 + g * 4 + 1);
     if (g > 0) t2_signal_group(&bars->a_grp[g - 1], lane);
     t2_store_a(c, cb, v);
-    TRACE2(6000 + p * 16 + g * 4 + 2);
+    TRACE2G(6000 + p * 16 + g * 4 + 2);
     sgn <<= 8;
   }
   t2_signal_group(&bars->a_grp[3], lane);
@@ -423,6 +428,9 @@ k_sdf_tc2(const DevScene sc, const DevNet net, const PointSource src, const uint
         }
       }
       if (!GRAD) {
+        // (the wait keeps grads_ready from completing twice before the helpers have looked at it)
+        if (it > 0) tc::mbar_wait(&bars->finish_done, (uint32_t)((it - 1) & 1));
+        tc::tc_fence_before();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&bars->grads_ready);       // this tile's smem operands may be restaged
         continue;
@@ -471,7 +479,7 @@ k_sdf_tc2(const DevScene sc, const DevNet net, const PointSource src, const uint
     // =============================== the MMA issuer ===============================
     const bool fast = (flags & 2) != 0;       // single fp16 MMA per product (opt-in reduced-precision mode)
     const bool nomma = (flags & 4) != 0;      // timing experiment: skip the tcgen05.mma instructions (results invalid)
-    if (lane == 0) {
+    if (tc::elect_one()) {
       const uint32_t ring = tc::smem_u32(smem + S2_RING);
       const uint32_t tAhi = tbase + T2_AHI, tAlo = tbase + T2_ALO;
       const uint32_t id128 = tc::idesc_f16(128, 128, 0), id160 = tc::idesc_f16(128, 160, 0), id32 = tc::idesc_f16(128, 32, 0);
@@ -517,6 +525,9 @@ k_sdf_tc2(const DevScene sc, const DevNet net, const PointSource src, const uint
           }
           if (!nomma) tc::mma_ss_w<true>(tD, a0 + 256, dh, w0 + 256, dh, id128);
           release_chunk();
+          // Every epilogue warp must have consumed the previous tile's last d_full phase (and read its D1 columns)
+          // before d_full completes again and before the next layer overwrites D1.
+          if (it > 0) tc::mbar_wait(&bars->grads_ready, (uint32_t)((it - 1) & 1));
           tc::mma_commit(&bars->d_full);
           TRACE2(70);
         }
@@ -538,14 +549,14 @@ k_sdf_tc2(const DevScene sc, const DevNet net, const PointSource src, const uint
               if (h == 0) tc::mma_ss_w<false>(tD, a0, dh, w0, dh, id128); else tc::mma_ss_w<true>(tD, a0, dh, w0, dh, id128);
             }
             release_chunk();
-            TRACE2(4000 + p * 8 + h);
+            TRACE2G(4000 + p * 8 + h);
           }
           // hidden columns: K chunk c needs column group c of the previous layer's epilogue
 #pragma unroll 1
           for (int c = 0; c < 4; ++c) {
             tc::mbar_wait(&bars->a_grp[c], ph_grp & 1);
             tc::tc_fence_after();
-            TRACE2(2000 + p * 8 + c);
+            TRACE2G(2000 + p * 8 + c);
             const uint32_t w0 = (uint32_t)d128 | next_chunk();
             const uint32_t ah = tAhi + c * 16, al = tAlo + c * 16;
             if (!nomma && !fast) {
@@ -572,7 +583,7 @@ k_sdf_tc2(const DevScene sc, const DevNet net, const PointSource src, const uint
           for (int c = 0; c < 4; ++c) {
             tc::mbar_wait(&bars->a_grp[c], ph_grp & 1);
             tc::tc_fence_after();
-            TRACE2(2000 + p * 8 + c);
+            TRACE2G(2000 + p * 8 + c);
             const uint32_t w0 = (uint32_t)d160 | next_chunk();
             const uint32_t ah = tAhi + c * 16, al = tAlo + c * 16;
             if (!nomma && !fast) {

@@ -9,6 +9,21 @@ namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One lane of a fully converged warp.  Code guarded by this predicate (rather than by `lane == 0`) lets ptxas know
+// that a single thread runs it: tcgen05.mma / commit operands then go to uniform registers with plain R2UR moves
+// instead of a per-instruction ELECT / R2UR.BROADCAST / BRA.U.ANY "waterfall" loop (~100 clk per MMA).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0, laneid = 0;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, %2;\n\t"
+      "@px mov.s32 %1, 1;\n\t"
+      "mov.s32 %0, rx;\n\t}"
+      : "+r"(laneid), "+r"(pred)
+      : "r"(0xFFFFFFFFu));
+  return pred != 0;
+}
+
 // ---- mbarrier ---------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
