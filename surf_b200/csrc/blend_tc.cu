@@ -62,7 +62,14 @@ struct BtBars {
   uint32_t tmem_base;
 };
 
-__device__ __forceinline__ float bt_elu(float x) { return x > 0.f ? x : (__expf(x) - 1.0f); }
+// ELU; the exponential is the bare MUFU.EX2 (flush-to-zero: exp underflows to 0 exactly where exp(x) - 1 == -1 in
+// fp32 anyway) — __expf wraps it in a denormal-range rescue that doubles the instruction count of the hottest
+// function of this kernel
+__device__ __forceinline__ float bt_elu(float x) {
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 1.4426950408889634f));
+  return x > 0.f ? x : e - 1.0f;
+}
 __device__ __forceinline__ float bt_sigmoid(float x) { return 1.0f / (1.0f + __expf(-x)); }
 
 // write 16 consecutive k values (k0 .. k0+15, k0 % 8 == 0) of row r into the canonical A operand
@@ -239,26 +246,54 @@ k_blend_tc(const uint8_t* __restrict__ wtc, const float* __restrict__ wf32, floa
       }
     }
     __syncthreads();
-    // ---- A operand of base_fc.0: [mean19, var19, x19, 0 x 7] ----
-    for (int it = tid; it < 19 * ppt; it += BT_THREADS) {      // weighted mean / variance over views (:15-19)
-      const int c = it / ppt, pp = it - c * ppt;
-      const int r0 = pp * V;
-      const float* x = F + c * BS + r0;
-      float mean = 0.f;
-      for (int v = 0; v < V; ++v) mean = fmaf(x[v], s_wv[r0 + v], mean);
-      float var = 0.f;
-      for (int v = 0; v < V; ++v) {
-        const float d = x[v] - mean;
-        var = fmaf(s_wv[r0 + v] * d, d, var);
+    // ---- A operand of base_fc.0: [mean19, var19, x19, 0 x 7]  (weighted mean / variance over the views, :15-19) ----
+    // thread (row, half) builds 32 consecutive k of its own row in registers and stores them as 16-byte vectors
+    // (conflict-free); the per-point statistics are recomputed by each of the point's V rows.
+    {
+      const int r0 = (r / V) * V;
+      const bool live = r < rows;
+      float vals[32];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) vals[k] = 0.f;
+      if (live) {
+        if (half == 0) {          // k 0..31 = mean 0..18, var 0..12
+#pragma unroll
+          for (int c = 0; c < 19; ++c) {
+            const float* x = F + c * BS + r0;
+            float mean = 0.f;
+            for (int v = 0; v < V; ++v) mean = fmaf(x[v], s_wv[r0 + v], mean);
+            vals[c] = mean;
+            if (c < 13) {
+              float var = 0.f;
+              for (int v = 0; v < V; ++v) {
+                const float d = x[v] - mean;
+                var = fmaf(s_wv[r0 + v] * d, d, var);
+              }
+              vals[19 + c] = var;
+            }
+          }
+        } else {                  // k 32..63 = var 13..18, x19, 0 x 7
+#pragma unroll
+          for (int c = 13; c < 19; ++c) {
+            const float* x = F + c * BS + r0;
+            float mean = 0.f;
+            for (int v = 0; v < V; ++v) mean = fmaf(x[v], s_wv[r0 + v], mean);
+            float var = 0.f;
+            for (int v = 0; v < V; ++v) {
+              const float d = x[v] - mean;
+              var = fmaf(s_wv[r0 + v] * d, d, var);
+            }
+            vals[c - 13] = var;
+          }
+#pragma unroll
+          for (int c = 0; c < 19; ++c) vals[6 + c] = F[c * BS + r];
+        }
       }
-      for (int v = 0; v < V; ++v) {
-        aop_put(aop, r0 + v, c, mean);
-        aop_put(aop, r0 + v, 19 + c, var);
-      }
-    }
-    {   // x19 -> k = 38..56, zeros -> 57..63 : thread (row, half) takes 13 of the 26 slots
-      const int k0 = half ? 51 : 38, k1 = half ? 64 : 51;
-      for (int k = k0; k < k1; ++k) aop_put(aop, r, k, k < 57 ? F[(k - 38) * BS + r] : 0.f);
+      float lo16[16], hi16[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) { lo16[k] = vals[k]; hi16[k] = vals[16 + k]; }
+      aop_store16(aop, r, half * 32, lo16);
+      aop_store16(aop, r, half * 32 + 16, hi16);
     }
     publish();
     // ---- base_fc.0 : 57(64) -> 64, ELU ----
