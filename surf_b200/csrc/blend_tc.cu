@@ -118,12 +118,15 @@ __device__ __forceinline__ void bt_issue(uint32_t tD, uint32_t aop_addr, uint32_
   tc::mma_commit(bar);
 }
 
+// VT: number of source views at compile time (2, 3, 4: the per-point loops over the views unroll) or 0 = runtime V
+template <int VT>
 __global__ void __launch_bounds__(BT_THREADS, 2)
 k_blend_tc(const uint8_t* __restrict__ wtc, const float* __restrict__ wf32, float s_abs, const float* __restrict__ feat,
-           const float* __restrict__ rdiff, const uint8_t* __restrict__ mask, int V, int packed19,
+           const float* __restrict__ rdiff, const uint8_t* __restrict__ mask, int V_rt, int packed19,
            const int32_t* __restrict__ list, const int32_t* __restrict__ count, int64_t n, float* __restrict__ rgb_out,
            uint8_t* __restrict__ views_out, int fast_i) {
   const bool fast = fast_i != 0;
+  const int V = VT ? VT : V_rt;
   extern __shared__ __align__(1024) uint8_t smem[];
   BtBars* bars = reinterpret_cast<BtBars*>(smem + SB_BAR);
   const float* WF = reinterpret_cast<const float*>(smem + SB_WF);
@@ -538,7 +541,10 @@ int launch_blend_tc(const surf_net* n, const float* d_feat, const float* d_raydi
                     uint8_t* d_views, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    SURF_CUDA(cudaFuncSetAttribute(k_blend_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SB_TOTAL));
+    SURF_CUDA(cudaFuncSetAttribute(k_blend_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SB_TOTAL));
+    SURF_CUDA(cudaFuncSetAttribute(k_blend_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SB_TOTAL));
+    SURF_CUDA(cudaFuncSetAttribute(k_blend_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SB_TOTAL));
+    SURF_CUDA(cudaFuncSetAttribute(k_blend_tc<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SB_TOTAL));
     attr_set = true;
   }
   if (n_pts <= 0) return 0;
@@ -547,9 +553,17 @@ int launch_blend_tc(const surf_net* n, const float* d_feat, const float* d_raydi
   const int64_t cap = (int64_t)n->n_sm * 2;
   const int grid = (int)(tiles < cap ? tiles : cap);
   surf_time_begin(3, st);
-  k_blend_tc<<<grid, BT_THREADS, SB_TOTAL, st>>>(n->blend_tc_w, n->blend_tc_f, n->dev.blend_s, d_feat, d_raydiff, d_mask, V,
-                                                 packed19 ? 1 : 0, list, count, n_pts, d_rgb, d_views,
-                                                 surf_mlp_mode() == 4 ? 1 : 0);
+#define BT_LAUNCH(VT)                                                                                                  \
+  k_blend_tc<VT><<<grid, BT_THREADS, SB_TOTAL, st>>>(n->blend_tc_w, n->blend_tc_f, n->dev.blend_s, d_feat, d_raydiff,   \
+                                                     d_mask, V, packed19 ? 1 : 0, list, count, n_pts, d_rgb, d_views,  \
+                                                     surf_mlp_mode() == 4 ? 1 : 0)
+  switch (V) {
+    case 2: BT_LAUNCH(2); break;
+    case 3: BT_LAUNCH(3); break;
+    case 4: BT_LAUNCH(4); break;
+    default: BT_LAUNCH(0); break;
+  }
+#undef BT_LAUNCH
   surf_time_end(3, st);
   SURF_LAUNCH_CHECK();
   return 0;
