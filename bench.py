@@ -50,7 +50,7 @@ def parse():
     ap.add_argument("--cpu-rays", type=int, default=8192, help="rays per CPU-baseline sample / reference-arm step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
-    ap.add_argument("--mlp-mode", type=int, default=1, choices=[0, 1, 3, 4],
+    ap.add_argument("--mlp-mode", type=int, default=1, choices=[0, 1, 3, 4, 5],
                     help="0 = fp32 FFMA MLP kernels, 1 = tcgen05 kernels with the fp16 hi/lo 3-MMA split (fp32-grade), "
                          "4 = tcgen05 single fp16 MMA (opt-in 1e-2 mode)")
     return ap.parse_args()

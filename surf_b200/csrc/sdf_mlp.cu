@@ -445,7 +445,7 @@ int surf_build_tc1_weights(const std::vector<std::vector<float>>& W, const surf_
 static int g_mlp_mode = 0;
 int surf_mlp_mode() { return g_mlp_mode; }
 extern "C" int surf_set_mlp_mode(int32_t mode) {
-  SURF_CHECK_ARG(mode >= 0 && mode <= 4, "mlp mode must be 0..4");
+  SURF_CHECK_ARG(mode >= 0 && mode <= 5, "mlp mode must be 0..5");
   g_mlp_mode = mode;
   return 0;
 }
@@ -593,6 +593,7 @@ int launch_sdf_mlp(const surf_scene* s, const surf_net* n, const PointSource& sr
       if (d_grad) return launch_sdf_tc1(s, n, src, d_sdf, d_grad, negate, st);
       return launch_sdf_tc_fwd(s, n, src, d_sdf, negate, st);
     }
+    if (g_mlp_mode == 5) return launch_sdf_tc3(s, n, src, d_sdf, d_grad, negate, st);
     return launch_sdf_tc2(s, n, src, d_sdf, d_grad, negate, st);
   }
   int64_t tiles = (src.n + MLP_TILE - 1) / MLP_TILE;

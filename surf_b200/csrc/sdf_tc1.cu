@@ -711,7 +711,8 @@ int surf_build_tc1_weights(const std::vector<std::vector<float>>& W, const surf_
   SURF_CUDA(cudaStreamSynchronize(st));
   net->tc1_blob = (const uint8_t*)p;
   // softplus' scratch: 5 layers x 4 x 512 threads x 16 B per CTA
-  rc = dev_alloc(net, &p, (size_t)net->n_sm * (5 * 4 * T1_EPI_THREADS + 5 * T1_EPI_THREADS / 4) * sizeof(uint4));
+  // (x 2: sdf_tc3.cu keeps two tiles in flight per CTA)
+  rc = dev_alloc(net, &p, (size_t)net->n_sm * 2 * (5 * 4 * T1_EPI_THREADS + 5 * T1_EPI_THREADS / 4) * sizeof(uint4));
   if (rc) return rc;
   net->tc1_scratch = p;
   return 0;

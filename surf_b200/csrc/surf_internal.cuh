@@ -290,6 +290,8 @@ struct T1Stream {
   uint32_t bytes[T1_MAXCHUNK];
 };
 extern T1Stream g_t1_stream;
+int launch_sdf_tc3(const surf_scene* s, const surf_net* n, const PointSource& src, float* d_sdf, float* d_grad,
+                   bool negate, cudaStream_t st);
 int launch_sdf_tc2(const surf_scene* s, const surf_net* n, const PointSource& src, float* d_sdf, float* d_grad,
                    bool negate, cudaStream_t st);
 int launch_sdf_tc1(const surf_scene* s, const surf_net* n, const PointSource& src, float* d_sdf, float* d_grad,

@@ -42,7 +42,7 @@ from surf_b200.modules.implicit_surface import ImplicitSurface  # noqa: E402
 
 
 # mode 1: the shipped tensor-core kernels (pipelined one-tile kernel, sdf_tc2.cu); mode 3: the first-generation ones
-@pytest.fixture(params=[1, 3])
+@pytest.fixture(params=[1, 3, 5])
 def tc_mode(request):
     _lib.set_mlp_mode(request.param)
     yield request.param
