@@ -13,7 +13,7 @@ import torch
 
 import surf_oracle as O
 from helpers import RTOL_FP32, assert_close, assert_equal_int, blend_envelope, load_golden, scene_from_recipe
-from surf_b200 import conf, synthetic
+from surf_b200 import _lib, conf, synthetic
 from surf_b200.modules import projector as P
 from surf_b200.modules.implicit_surface import ImplicitSurface
 
@@ -349,7 +349,17 @@ def test_validate_image_vs_reference():
 # ------------------------------------------------------------------------------------------------
 # size-independent properties on a larger scene
 # ------------------------------------------------------------------------------------------------
-def test_properties_larger_scene():
+@pytest.mark.parametrize("mlp_mode", [0, 1, 5])
+def test_properties_larger_scene(mlp_mode):
+    """Size-independent properties, in the fp32 FFMA mode and in both tensor-core kernel families."""
+    _lib.set_mlp_mode(mlp_mode)
+    try:
+        _properties_larger_scene()
+    finally:
+        _lib.set_mlp_mode(0)
+
+
+def _properties_larger_scene():
     sc = synthetic.make_scene(3, 144, 200, 16, seed=4)
     g = load_golden("render_v2_perturbed")
     m = build(g)
