@@ -91,14 +91,6 @@ __device__ __forceinline__ void aop_store8(uint8_t* aop, int r, int k0, const fl
   *reinterpret_cast<uint4*>(p) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
   *reinterpret_cast<uint4*>(p + 16384) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
-__device__ __forceinline__ void aop_put(uint8_t* aop, int r, int k, float v) {
-  const __half h = __float2half_rn(v);
-  const __half l = __float2half_rn(v - __half2float(h));
-  const uint32_t off = (uint32_t)(k >> 3) * 2048u + r * 16 + (k & 7) * 2;
-  *reinterpret_cast<__half*>(aop + off) = h;
-  *reinterpret_cast<__half*>(aop + 16384 + off) = l;
-}
-
 // one layer on the tensor core: D[128 x N] = A_op[128 x K] * W^T, issued by one thread
 template <int N, int KSTEPS>
 __device__ __forceinline__ void bt_issue(uint32_t tD, uint32_t aop_addr, uint32_t w_addr, uint64_t* bar, bool fast) {

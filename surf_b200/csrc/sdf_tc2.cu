@@ -115,14 +115,6 @@ __device__ __forceinline__ float t2_decode_u(uint32_t pair) {
   return __uint_as_float(__byte_perm(pair, 0x43000000u, T ? 0x7632 : 0x7610)) - 127.0f;
 }
 
-// chunks per layer phase of the weight stream: phases 0..5 forward, 6..10 reverse lin5..lin1, 11 reverse lin0
-__device__ __forceinline__ int t2_phase_chunks(int phase) {
-  if (phase == 0) return 1;
-  if (phase < 6) return 6;      // 2 x K16 (features | bias) first, then 4 x K32 hidden
-  if (phase < 11) return 4;
-  return 2;
-}
-
 struct T2Epi {
   uint32_t tl;            // TMEM base of my lane quarter
   int part, r, te;
