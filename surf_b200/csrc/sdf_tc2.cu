@@ -198,12 +198,12 @@ __device__ __forceinline__ void t2_store_a(const T2Epi& c, int cb, const float (
   tc::tmem_st4(c.tl + T2_ALO + (cb >> 1), lo);
 }
 
-// group g of the next A operand is in TMEM: one arrival per warp
-__device__ __forceinline__ void t2_signal_group(uint64_t* bar, int lane) {
+// group g of the next A operand is in TMEM: one arrival per warp (bar_addr: shared-window address of a_grp[g])
+__device__ __forceinline__ void t2_signal_group(uint32_t bar_addr, int lane) {
   tc::tmem_wait_st();
   tc::tc_fence_before();
   __syncwarp();
-  if (lane == 0) tc::mbar_arrive(bar);
+  if (lane == 0) tc::mbar_arrive_addr(bar_addr);
 }
 
 // wait for the outstanding tcgen05.ld; the registers it fills are operands so that no use can be scheduled above it
@@ -214,46 +214,67 @@ __device__ __forceinline__ void t2_wait_ld(uint32_t (&r)[8]) {
                : "memory");
 }
 
-// The group loops below are deliberately NOT unrolled: inside one basic block ptxas hoists the MUFU work of all four
-// groups to the front and the first group would be signalled when half of the layer is done (measured).  They are
-// software-pipelined by hand instead: the accumulator columns of group g+1 are requested before group g is computed,
-// and group g-1 is signalled (tcgen05.wait::st + arrive) after the MUFU part of group g, when its TMEM stores have long
-// landed — a warp never sits on a TMEM round trip with nothing to issue.
+// The group loops below are deliberately NOT fully unrolled: inside one basic block ptxas hoists the MUFU work of all
+// four groups to the front and the first group would be signalled when half of the layer is done (measured).  They
+// are software-pipelined by hand instead, two groups per iteration on two alternating register sets (no copies): the
+// accumulator columns of group g+1 are requested before group g is computed, and group g-1 is signalled
+// (tcgen05.wait::st + arrive) after the MUFU part of group g, when its TMEM stores have long landed — a warp never
+// sits on a TMEM round trip with nothing to issue.
 template <bool GRAD, bool HEAD>
 __device__ __forceinline__ void t2_fwd_layer(const T2Epi& c, T2Bars* bars, int l, bool skip_next, float& head, int lane,
                                              uint8_t* smem, int& trace_n, int trace_slot) {
   const uint32_t dcol = c.tl + ((l & 1) ? T2_D1 : T2_D0) + c.part * 8;
+  const uint32_t bar0 = tc::smem_u32(&bars->a_grp[0]);
   constexpr bool SIGNAL = !HEAD || GRAD;
+  const bool dbg_noact = (c.dbg & 8) != 0, dbg_noscratch = (c.dbg & 16) != 0;
   uint32_t sgn = 0;
-  uint32_t dn[8];
-  tc::tmem_ld8(dcol, dn);
+  uint32_t da[8], db[8];
+  tc::tmem_ld8(dcol, da);
 #pragma unroll 1
-  for (int g = 0; g < 4; ++g) {
-    t2_wait_ld(dn);
-    uint32_t dv[8];
+  for (int i = 0; i < 2; ++i) {
+    {   // ---- group 2i from `da`; group 2i+1 in flight into `db` ----
+      const int g = 2 * i, cb = g * 32 + c.part * 8;
+      t2_wait_ld(da);
+      tc::tmem_ld8(dcol + (g + 1) * 32, db);
+      TRACE2G(6000 + l * 16 + g * 4);
+      uint4 spw = make_uint4(0u, 0u, 0u, 0u);
+      float h[8];
+      if (dbg_noact) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) dv[j] = dn[j];
-    if (g < 3) tc::tmem_ld8(dcol + (g + 1) * 32, dn);
-    TRACE2G(6000 + l * 16 + g * 4);
-    const int cb = g * 32 + c.part * 8;
-    uint4 spw = make_uint4(0u, 0u, 0u, 0u);
-    float h[8];
-    if (!HEAD && g == 3 && skip_next) {
-      if (c.part == 0) t2_fwd_act<GRAD, 1, false>(c, cb, dv, h, spw, sgn, head);
-      else t2_fwd_act<GRAD, 2, false>(c, cb, dv, h, spw, sgn, head);
-    } else if (c.dbg & 8) {
-#pragma unroll
-      for (int n = 0; n < 8; ++n) h[n] = __uint_as_float(dv[n]);
-    } else {
-      t2_fwd_act<GRAD, 0, HEAD>(c, cb, dv, h, spw, sgn, head);
+        for (int n = 0; n < 8; ++n) h[n] = __uint_as_float(da[n]);
+      } else {
+        t2_fwd_act<GRAD, 0, HEAD>(c, cb, da, h, spw, sgn, head);
+      }
+      TRACE2G(6000 + l * 16 + g * 4 + 1);
+      if (SIGNAL && i > 0) t2_signal_group(bar0 + (g - 1) * 8, lane);
+      if (SIGNAL) t2_store_a(c, cb, h);
+      TRACE2G(6000 + l * 16 + g * 4 + 2);
+      if (GRAD && !HEAD && !dbg_noscratch) c.scratch[(size_t)(l * 4 + g) * T2_EPI_THREADS + c.te] = spw;
     }
-    TRACE2G(6000 + l * 16 + g * 4 + 1);
-    if (SIGNAL && g > 0) t2_signal_group(&bars->a_grp[g - 1], lane);
-    if (SIGNAL) t2_store_a(c, cb, h);
-    TRACE2G(6000 + l * 16 + g * 4 + 2);
-    if (GRAD && !HEAD && !(c.dbg & 16)) c.scratch[(size_t)(l * 4 + g) * T2_EPI_THREADS + c.te] = spw;
+    {   // ---- group 2i+1 from `db`; group 2i+2 in flight into `da` ----
+      const int g = 2 * i + 1, cb = g * 32 + c.part * 8;
+      t2_wait_ld(db);
+      if (i == 0) tc::tmem_ld8(dcol + (g + 1) * 32, da);
+      TRACE2G(6000 + l * 16 + g * 4);
+      uint4 spw = make_uint4(0u, 0u, 0u, 0u);
+      float h[8];
+      if (!HEAD && i == 1 && skip_next) {
+        if (c.part == 0) t2_fwd_act<GRAD, 1, false>(c, cb, db, h, spw, sgn, head);
+        else t2_fwd_act<GRAD, 2, false>(c, cb, db, h, spw, sgn, head);
+      } else if (dbg_noact) {
+#pragma unroll
+        for (int n = 0; n < 8; ++n) h[n] = __uint_as_float(db[n]);
+      } else {
+        t2_fwd_act<GRAD, 0, HEAD>(c, cb, db, h, spw, sgn, head);
+      }
+      TRACE2G(6000 + l * 16 + g * 4 + 1);
+      if (SIGNAL) t2_signal_group(bar0 + (g - 1) * 8, lane);
+      if (SIGNAL) t2_store_a(c, cb, h);
+      TRACE2G(6000 + l * 16 + g * 4 + 2);
+      if (GRAD && !HEAD && !dbg_noscratch) c.scratch[(size_t)(l * 4 + g) * T2_EPI_THREADS + c.te] = spw;
+    }
   }
-  if (SIGNAL) t2_signal_group(&bars->a_grp[3], lane);
+  if (SIGNAL) t2_signal_group(bar0 + 3 * 8, lane);
   if (GRAD && !HEAD) c.sgn_scratch[(size_t)l * T2_EPI_THREADS + c.te] = sgn;
 }
 
@@ -262,43 +283,62 @@ __device__ __forceinline__ void t2_fwd_layer(const T2Epi& c, T2Bars* bars, int l
 __device__ __forceinline__ void t2_bwd_layer(const T2Epi& c, T2Bars* bars, int p, bool skip_pe, int lsrc, float (&gf)[8],
                                              int lane, uint8_t* smem, int& trace_n, int trace_slot) {
   const uint32_t dbase = c.tl + ((p & 1) ? T2_D1 : T2_D0) + c.part * 8;
+  const uint32_t bar0 = tc::smem_u32(&bars->a_grp[0]);
+  const bool dbg_noact = (c.dbg & 8) != 0, dbg_noscratch = (c.dbg & 16) != 0;
+  const uint4* codes = c.scratch + (size_t)(lsrc * 4) * T2_EPI_THREADS + c.te;
   uint32_t sgn = c.sgn_scratch[(size_t)lsrc * T2_EPI_THREADS + c.te];
-  uint4 spw = c.scratch[(size_t)(lsrc * 4) * T2_EPI_THREADS + c.te];
-  uint32_t dn[8];
-  tc::tmem_ld8(dbase, dn);
+  uint4 spa = codes[0], spb = make_uint4(0u, 0u, 0u, 0u);
+  uint32_t da[8], db[8];
+  tc::tmem_ld8(dbase, da);
 #pragma unroll 1
-  for (int g = 0; g < 4; ++g) {
-    t2_wait_ld(dn);
-    uint32_t dv[8];
+  for (int i = 0; i < 2; ++i) {
+    {   // ---- group 2i from `da` / codes `spa`; group 2i+1 in flight ----
+      const int g = 2 * i, cb = g * 32 + c.part * 8;
+      t2_wait_ld(da);
+      tc::tmem_ld8(dbase + (g + 1) * 32, db);
+      if (!dbg_noscratch) spb = codes[(size_t)(g + 1) * T2_EPI_THREADS];
+      TRACE2G(6000 + p * 16 + g * 4);
+      float v[8];
+      if (dbg_noact) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) dv[j] = dn[j];
-    tc::tmem_ld8(dbase + (g + 1) * 32, dn);               // g == 3: the feature-gradient columns 128 + part*8 ..
-    TRACE2G(6000 + p * 16 + g * 4);
-    const uint4 spw_cur = spw;
-    if (g < 3 && !(c.dbg & 16)) spw = c.scratch[(size_t)(lsrc * 4 + g + 1) * T2_EPI_THREADS + c.te];     // next group's codes
-    const int cb = g * 32 + c.part * 8;
-    float v[8];
-    if (g == 3 && skip_pe) {
-      if (c.part == 0) t2_bwd_act<1>(c, cb, dv, spw_cur, sgn, v);
-      else t2_bwd_act<2>(c, cb, dv, spw_cur, sgn, v);
-    } else if (c.dbg & 8) {
-#pragma unroll
-      for (int n = 0; n < 8; ++n) v[n] = __uint_as_float(dv[n]);
-    } else {
-      t2_bwd_act<0>(c, cb, dv, spw_cur, sgn, v);
+        for (int n = 0; n < 8; ++n) v[n] = __uint_as_float(da[n]);
+      } else {
+        t2_bwd_act<0>(c, cb, da, spa, sgn, v);
+      }
+      TRACE2G(6000 + p * 16 + g * 4 + 1);
+      if (i > 0) t2_signal_group(bar0 + (g - 1) * 8, lane);
+      t2_store_a(c, cb, v);
+      TRACE2G(6000 + p * 16 + g * 4 + 2);
+      sgn <<= 8;
     }
-    TRACE2G(6000 + p * 16 + g * 4 + 1);
-    if (g > 0) t2_signal_group(&bars->a_grp[g - 1], lane);
-    t2_store_a(c, cb, v);
-    TRACE2G(6000 + p * 16 + g * 4 + 2);
-    sgn <<= 8;
-  }
-  t2_signal_group(&bars->a_grp[3], lane);
-  t2_wait_ld(dn);
+    {   // ---- group 2i+1 from `db` / codes `spb`; group 2i+2 (i == 1: the feature-gradient columns 128 ..) in flight ----
+      const int g = 2 * i + 1, cb = g * 32 + c.part * 8;
+      t2_wait_ld(db);
+      tc::tmem_ld8(dbase + (g + 1) * 32, da);
+      if (i == 0 && !dbg_noscratch) spa = codes[(size_t)(g + 1) * T2_EPI_THREADS];
+      TRACE2G(6000 + p * 16 + g * 4);
+      float v[8];
+      if (i == 1 && skip_pe) {
+        if (c.part == 0) t2_bwd_act<1>(c, cb, db, spb, sgn, v);
+        else t2_bwd_act<2>(c, cb, db, spb, sgn, v);
+      } else if (dbg_noact) {
 #pragma unroll
-  for (int j = 0; j < 8; ++j) gf[j] += __uint_as_float(dn[j]);
+        for (int n = 0; n < 8; ++n) v[n] = __uint_as_float(db[n]);
+      } else {
+        t2_bwd_act<0>(c, cb, db, spb, sgn, v);
+      }
+      TRACE2G(6000 + p * 16 + g * 4 + 1);
+      t2_signal_group(bar0 + (g - 1) * 8, lane);
+      t2_store_a(c, cb, v);
+      TRACE2G(6000 + p * 16 + g * 4 + 2);
+      sgn <<= 8;
+    }
+  }
+  t2_signal_group(bar0 + 3 * 8, lane);
+  t2_wait_ld(da);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) gf[j] += __uint_as_float(da[j]);
 }
-
 
 template <bool GRAD>
 __global__ void __launch_bounds__(T2_THREADS, 1)
