@@ -30,7 +30,7 @@ __device__ __forceinline__ void bilinear_taps(float x, float y, int w, int h, in
 }
 
 // one thread per (point, source view)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 k_lookup_feature(const DevScene sc, const PointSource src, float* __restrict__ feat_out, float* __restrict__ rd_out,
                  uint8_t* __restrict__ mask_out, int packed19) {
   int64_t n_total = src.n;
