@@ -22,7 +22,7 @@ int surf_flags_pass(const surf_scene* s, const surf_render_cfg* cfg, const float
 
 __device__ __forceinline__ float sigmoid_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
 
-__global__ void __launch_bounds__(COMP_WARPS * 32)
+__global__ void __launch_bounds__(COMP_WARPS * 32, 4)
 k_composite(const DevScene sc, int64_t B, int S, float sample_dist, float inv_s, float cos_anneal,
             const float* __restrict__ rays_o, const float* __restrict__ rays_d, const float* __restrict__ z_vals,
             const uint8_t* __restrict__ flags, const float* __restrict__ sdf, const float* __restrict__ grad,
