@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define SURF_ABI_VERSION 1
+#define SURF_ABI_VERSION 2
 #define SURF_MAX_LEVELS 4
 #define SURF_MAX_VIEWS 8       /* source views (nv-1) */
 #define SURF_MAX_STAGES 4
@@ -78,6 +78,21 @@ typedef struct surf_scene_stats {
 int surf_scene_create(const surf_scene_inputs* in, void* stream, surf_scene** out);
 void surf_scene_destroy(surf_scene* s);
 int surf_scene_get_stats(const surf_scene* s, surf_scene_stats* out);
+/* The per-batch part of a scene: source images, feature pyramids and cameras (the `ipts` keys imgs / intrs / c2ws
+ * and the feature lists of surf.py:138-159).  surf_scene_create installs them when given; surf_scene_set_views
+ * replaces them on a live scene without touching the (multi-GB) volume part, e.g. when SuRF.forward selects other
+ * `view_ids` (surf.py:140-146).  d_imgs may be NULL (cameras only).  Stream-ordered. */
+typedef struct surf_scene_views {
+  int32_t n_views;                              /* nv */
+  int32_t img_h, img_w;
+  int32_t n_feat_levels;                        /* 4 */
+  const float* d_imgs;                          /* (nv,3,H,W) */
+  const float* d_features[4];                   /* (nv,4,H>>i,W>>i) NCHW */
+  const float* h_intrs;                         /* HOST (nv,4,4) */
+  const float* h_w2cs;                          /* HOST (nv,4,4) = inverse(c2ws) */
+  const float* h_c2ws;                          /* HOST (nv,4,4) */
+} surf_scene_views;
+int surf_scene_set_views(surf_scene* s, const surf_scene_views* in, void* stream);
 /* finetune mode optimises volumes[l] in place (surf.py:43-44,72): refresh the padded copy */
 int surf_scene_update_volume(surf_scene* s, int32_t level, const float* d_volume, int64_t n_vox, void* stream);
 
@@ -107,6 +122,19 @@ typedef struct surf_net_inputs {
 int surf_net_create(const surf_net_inputs* in, void* stream, surf_net** out);
 void surf_net_destroy(surf_net* n);
 
+/* ---- MLP kernel family, chosen PER CALL (no process-wide state) ---------------------------------
+ *   SURF_MLP_FFMA    fp32 CUDA-core kernels (sdf_mlp.cu, blend.cu): the parity anchor written first;
+ *   SURF_MLP_TC      tcgen05 / TMEM kernels (sdf_tc2.cu, blend_tc.cu), every product as the fp16 hi/lo 3-MMA
+ *                    split with fp32 accumulation: fp32-grade (1e-4) and bitwise reproducible.  This is what the
+ *                    Python mirror passes by default and what bench.py measures;
+ *   SURF_MLP_TC_FAST the same kernels with ONE fp16 MMA per product: the opt-in reduced-precision mode
+ *                    (north_star: 1e-2 relative).
+ * A network whose shape the tensor-core kernels do not support (multires != 4 or skip layer != 3) runs the
+ * FFMA kernels whatever the mode. */
+#define SURF_MLP_FFMA 0
+#define SURF_MLP_TC 1
+#define SURF_MLP_TC_FAST 4
+
 /* ---- render configuration (confs/surf.conf: model.implicit_surface.render) ---------------- */
 typedef struct surf_render_cfg {
   int32_t n_stages;                        /* 4 */
@@ -120,7 +148,7 @@ typedef struct surf_render_cfg {
   const float* d_lin_tables;               /* torch.linspace(0,1,n) for n = n_samples[0..], then n_depth,
                                               concatenated (host-generated: linspace is not reproducible by
                                               a device formula) */
-  int32_t mlp_mode;                        /* reserved, ignored: the kernel family is process-wide, surf_set_mlp_mode */
+  int32_t mlp_mode;                        /* SURF_MLP_* kernel family for the SDF / blending MLPs of THIS call */
 } surf_render_cfg;
 
 /* Outputs of render_core; any pointer may be NULL (not written).  Shapes use B rays, S samples,
@@ -172,7 +200,7 @@ int surf_render_rays(const surf_scene* s, const surf_net* n, const surf_render_c
 /* SDFNetworkSparse.sdf / .gradient (sdf_network.py:123-141) on a flat point list.
  * d_sdf (n,) required; d_grad (n,3) nullable (forward only when NULL). */
 int surf_sdf_points(const surf_scene* s, const surf_net* n, const float* d_pts, int64_t n_pts, float* d_sdf,
-                    float* d_grad, void* stream);
+                    float* d_grad, int32_t mlp_mode, void* stream);
 
 /* extract_geometry's SDF query (implicit_surface.py:337-351): u[x,y,z] = -sdf(xs[x],ys[y],zs[z]) on the
  * tensor-product grid of the three coordinate tables (host torch.linspace, uploaded).  Dense (Q16).
@@ -180,7 +208,7 @@ int surf_sdf_points(const surf_scene* s, const surf_net* n, const float* d_pts, 
  * get `fill` instead of an MLP evaluation (NOT result-identical outside the mask). */
 int surf_sdf_grid(const surf_scene* s, const surf_net* n, const float* d_xs, int32_t nx, const float* d_ys,
                   int32_t ny, const float* d_zs, int32_t nz, float* d_u, int32_t sparsify, float fill,
-                  void* stream);
+                  int32_t mlp_mode, void* stream);
 
 /* ---- stage-isolated entry points (parity tests; same kernels/device functions) ------------ */
 /* lookup_volume(pts, mask_volumes, 'nearest').any(-1)  (projector.py:392-420, implicit_surface.py:86) */
@@ -192,7 +220,7 @@ int surf_lookup_feature(const surf_scene* s, const float* d_pts, int64_t n_pts, 
                         float* d_ray_diff, uint8_t* d_mask, void* stream);
 /* BlendingNetwork.forward (blending_network.py:69-117) on given inputs -> rgb (n,3) */
 int surf_blend(const surf_net* n, const float* d_feat_views, const float* d_ray_diff, const uint8_t* d_mask,
-               int64_t n_pts, int32_t n_src_views, float* d_rgb, void* stream);
+               int64_t n_pts, int32_t n_src_views, float* d_rgb, int32_t mlp_mode, void* stream);
 /* render_core lines 75-89: z_vals -> mid_z (B,S), flags (P,) with the per-chunk fallback applied */
 int surf_point_flags(const surf_scene* s, const surf_render_cfg* cfg, const float* d_rays_o, const float* d_rays_d,
                      const float* d_z_vals, int64_t n_rays, int32_t n_samples_total, float* d_mid_z,
@@ -211,17 +239,6 @@ int64_t surf_launch_count(void);
 #define SURF_TIMING_KINDS 7
 int surf_timing_enable(int32_t on);
 int surf_timing_read(double* ms_out /*[SURF_TIMING_KINDS]*/, int64_t* launches_out /*[SURF_TIMING_KINDS]*/);
-
-/* Process-wide choice of the SDF-MLP / blending kernel family:
- *   0 = fp32 FFMA (default);
- *   1 = tcgen05 tensor cores with the fp16 hi/lo 3-MMA split (fp32-grade accuracy, bitwise reproducible): the
- *       pipelined one-tile kernel of sdf_tc2.cu for forward-only and forward + gradient queries, blend_tc.cu;
- *   3 = the first-generation tensor-core kernels (sdf_tc.cu forward, sdf_tc1.cu forward + gradient), kept for
- *       comparison; 2 = mode 3 with two MMA-issuing threads per tile in the forward kernel (experimental: the fp32
- *       accumulation order then depends on timing);
- *   4 = mode 1 with ONE fp16 MMA per product (opt-in reduced precision, 1e-2 relative).
- * Kernels without a tensor-core edition keep using mode 0.  surf_render_cfg.mlp_mode is not consulted. */
-int surf_set_mlp_mode(int32_t mode);
 
 /* Diagnostic: one 128 x N x K GEMM through the tcgen05 building blocks of the tensor-core MLP kernels
  * (A operand in TMEM, B in shared memory, fp32 accumulate in TMEM).  D (128,N) = A (128,K) * B (N,K)^T,

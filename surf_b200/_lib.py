@@ -14,6 +14,13 @@ MAX_LEVELS = 4
 MAX_VIEWS = 8
 MAX_STAGES = 4
 SDF_LAYERS = 7
+ABI_VERSION = 2
+
+# MLP kernel family, chosen per call (include/surf_b200.h SURF_MLP_*)
+MLP_FFMA = 0        # fp32 CUDA-core kernels: the parity anchor
+MLP_TC = 1          # tcgen05 / TMEM kernels, fp16 hi/lo 3-MMA split: fp32-grade, the default of the Python mirror
+MLP_TC_FAST = 4     # tcgen05, one fp16 MMA per product: opt-in reduced precision (1e-2)
+MLP_MODES = (MLP_FFMA, MLP_TC, MLP_TC_FAST)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libsurf_b200.so")
@@ -21,11 +28,12 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libsurf_b200.so")
 EXPORTS = [
     "surf_version", "surf_last_error", "surf_launch_count", "surf_timing_enable", "surf_timing_read",
     "surf_scene_create", "surf_scene_destroy", "surf_scene_get_stats", "surf_scene_update_volume",
+    "surf_scene_set_views",
     "surf_net_create", "surf_net_destroy",
     "surf_render_workspace_bytes", "surf_sample_rays", "surf_render_core", "surf_render_rays",
     "surf_sdf_points", "surf_sdf_grid",
     "surf_point_mask", "surf_lookup_sparse", "surf_lookup_feature", "surf_blend", "surf_point_flags",
-    "surf_tc_selftest", "surf_set_mlp_mode",
+    "surf_tc_selftest",
 ]
 
 
@@ -40,6 +48,20 @@ class SceneInputs(C.Structure):
         ("d_mask_volumes", C.c_void_p * MAX_LEVELS),
         ("d_matching_volume", C.c_void_p),
         ("match_dim", C.c_int32),
+        ("n_views", C.c_int32),
+        ("img_h", C.c_int32),
+        ("img_w", C.c_int32),
+        ("n_feat_levels", C.c_int32),
+        ("d_imgs", C.c_void_p),
+        ("d_features", C.c_void_p * 4),
+        ("h_intrs", C.c_void_p),
+        ("h_w2cs", C.c_void_p),
+        ("h_c2ws", C.c_void_p),
+    ]
+
+
+class SceneViews(C.Structure):
+    _fields_ = [
         ("n_views", C.c_int32),
         ("img_h", C.c_int32),
         ("img_w", C.c_int32),
@@ -130,6 +152,8 @@ def _declare(lib):
     lib.surf_scene_get_stats.argtypes = [vp, P(SceneStats)]
     lib.surf_scene_update_volume.restype = C.c_int
     lib.surf_scene_update_volume.argtypes = [vp, i32, vp, i64, vp]
+    lib.surf_scene_set_views.restype = C.c_int
+    lib.surf_scene_set_views.argtypes = [vp, P(SceneViews), vp]
     lib.surf_net_create.restype = C.c_int
     lib.surf_net_create.argtypes = [P(NetInputs), vp, P(vp)]
     lib.surf_net_destroy.restype = None
@@ -144,9 +168,9 @@ def _declare(lib):
     lib.surf_render_rays.argtypes = [vp, vp, P(RenderCfg), vp, vp, vp, vp, vp, i64, P(RenderOutputs), vp,
                                      C.c_size_t, vp]
     lib.surf_sdf_points.restype = C.c_int
-    lib.surf_sdf_points.argtypes = [vp, vp, vp, i64, vp, vp, vp]
+    lib.surf_sdf_points.argtypes = [vp, vp, vp, i64, vp, vp, i32, vp]
     lib.surf_sdf_grid.restype = C.c_int
-    lib.surf_sdf_grid.argtypes = [vp, vp, vp, i32, vp, i32, vp, i32, vp, i32, f32, vp]
+    lib.surf_sdf_grid.argtypes = [vp, vp, vp, i32, vp, i32, vp, i32, vp, i32, f32, i32, vp]
     lib.surf_point_mask.restype = C.c_int
     lib.surf_point_mask.argtypes = [vp, vp, i64, vp, vp]
     lib.surf_lookup_sparse.restype = C.c_int
@@ -154,9 +178,7 @@ def _declare(lib):
     lib.surf_lookup_feature.restype = C.c_int
     lib.surf_lookup_feature.argtypes = [vp, vp, i64, vp, vp, vp, vp]
     lib.surf_blend.restype = C.c_int
-    lib.surf_blend.argtypes = [vp, vp, vp, vp, i64, i32, vp, vp]
-    lib.surf_set_mlp_mode.restype = C.c_int
-    lib.surf_set_mlp_mode.argtypes = [i32]
+    lib.surf_blend.argtypes = [vp, vp, vp, vp, i64, i32, vp, i32, vp]
     lib.surf_tc_selftest.restype = C.c_int
     lib.surf_tc_selftest.argtypes = [vp, vp, vp, i32, i32, i32, vp]
     lib.surf_point_flags.restype = C.c_int
@@ -180,7 +202,7 @@ def load():
         if missing:
             raise RuntimeError("surf_b200: library lacks symbols: %s" % ", ".join(missing))
         _declare(lib)
-        if lib.surf_version() != 1:
+        if lib.surf_version() != ABI_VERSION:
             raise RuntimeError("surf_b200: ABI version mismatch")
         _lib = lib
     return _lib
@@ -209,9 +231,3 @@ def timing_read():
     n = (C.c_int64 * len(TIMING_KINDS))()
     check(load().surf_timing_read(ms, n), "timing_read")
     return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(TIMING_KINDS)}
-
-
-def set_mlp_mode(mode: int):
-    """0 = fp32 FFMA kernels, 1 = tcgen05 tensor-core kernels (fp16 hi/lo split, fp32-grade accuracy),
-    3 = first-generation tensor-core kernels (comparison), 4 = single-MMA reduced precision (see include/surf_b200.h)."""
-    check(load().surf_set_mlp_mode(int(mode)), "set_mlp_mode")

@@ -528,17 +528,16 @@ int launch_lookup_feature(const surf_scene* s, const PointSource& src, float* d_
 
 int launch_blend(const surf_scene*, const surf_net* n, const float* d_feat, const float* d_raydiff,
                  const uint8_t* d_mask, int V, bool packed19, const int32_t* list, const int32_t* count, int64_t n_pts,
-                 float* d_rgb, uint8_t* d_views, cudaStream_t st) {
-  static bool attr_set = false;
-  const size_t smem = (size_t)(BS_W + blend_offsets().total) * sizeof(float);
-  if (!attr_set) {
-    SURF_CUDA(cudaFuncSetAttribute(k_blend, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+                 float* d_rgb, uint8_t* d_views, int mode, cudaStream_t st) {
   if (n_pts <= 0) return 0;
   SURF_CHECK_ARG(V >= 1 && V <= SURF_MAX_VIEWS, "n_src_views");
-  if (surf_mlp_mode() >= 1)
-    return launch_blend_tc(n, d_feat, d_raydiff, d_mask, V, packed19, list, count, n_pts, d_rgb, d_views, st);
+  SURF_CHECK_ARG(mode == SURF_MLP_FFMA || mode == SURF_MLP_TC || mode == SURF_MLP_TC_FAST, "mlp_mode must be SURF_MLP_FFMA, SURF_MLP_TC or SURF_MLP_TC_FAST");
+  if (mode != SURF_MLP_FFMA)
+    return launch_blend_tc(n, d_feat, d_raydiff, d_mask, V, packed19, list, count, n_pts, d_rgb, d_views,
+                           mode == SURF_MLP_TC_FAST, st);
+  const size_t smem = (size_t)(BS_W + blend_offsets().total) * sizeof(float);
+  int rc = surf_ensure_dyn_smem((const void*)k_blend, (int)smem);
+  if (rc) return rc;
   const int ppt = BL_ROWS / V;
   int64_t tiles = (n_pts + ppt - 1) / ppt;
   const int grid = (int)(tiles < n->n_sm ? tiles : n->n_sm);
@@ -562,9 +561,9 @@ extern "C" int surf_lookup_feature(const surf_scene* s, const float* d_pts, int6
 }
 
 extern "C" int surf_blend(const surf_net* n, const float* d_feat_views, const float* d_ray_diff, const uint8_t* d_mask,
-                          int64_t n_pts, int32_t n_src_views, float* d_rgb, void* stream) {
+                          int64_t n_pts, int32_t n_src_views, float* d_rgb, int32_t mlp_mode, void* stream) {
   SURF_CHECK_ARG(n && d_feat_views && d_ray_diff && d_mask && d_rgb, "null pointer");
   SURF_CHECK_ARG(n_src_views >= 1 && n_src_views <= SURF_MAX_VIEWS, "n_src_views");
   return launch_blend(nullptr, n, d_feat_views, d_ray_diff, d_mask, n_src_views, true, nullptr, nullptr, n_pts, d_rgb,
-                      nullptr, (cudaStream_t)stream);
+                      nullptr, mlp_mode, (cudaStream_t)stream);
 }

@@ -530,16 +530,16 @@ int surf_build_blend_tc_weights(const surf_net_inputs* in, surf_net* net, cudaSt
 
 int launch_blend_tc(const surf_net* n, const float* d_feat, const float* d_raydiff, const uint8_t* d_mask, int V,
                     bool packed19, const int32_t* list, const int32_t* count, int64_t n_pts, float* d_rgb,
-                    uint8_t* d_views, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    SURF_CUDA(cudaFuncSetAttribute(k_blend_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SB_TOTAL));
-    SURF_CUDA(cudaFuncSetAttribute(k_blend_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SB_TOTAL));
-    SURF_CUDA(cudaFuncSetAttribute(k_blend_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SB_TOTAL));
-    SURF_CUDA(cudaFuncSetAttribute(k_blend_tc<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SB_TOTAL));
-    attr_set = true;
-  }
+                    uint8_t* d_views, bool fast, cudaStream_t st) {
   if (n_pts <= 0) return 0;
+  {
+    const void* fns[4] = {(const void*)k_blend_tc<0>, (const void*)k_blend_tc<2>, (const void*)k_blend_tc<3>,
+                          (const void*)k_blend_tc<4>};
+    for (int i = 0; i < 4; ++i) {
+      const int rc = surf_ensure_dyn_smem(fns[i], SB_TOTAL);
+      if (rc) return rc;
+    }
+  }
   const int ppt = BT_ROWS / V;
   const int64_t tiles = (n_pts + ppt - 1) / ppt;
   const int64_t cap = (int64_t)n->n_sm * 2;
@@ -548,7 +548,7 @@ int launch_blend_tc(const surf_net* n, const float* d_feat, const float* d_raydi
 #define BT_LAUNCH(VT)                                                                                                  \
   k_blend_tc<VT><<<grid, BT_THREADS, SB_TOTAL, st>>>(n->blend_tc_w, n->blend_tc_f, n->dev.blend_s, d_feat, d_raydiff,   \
                                                      d_mask, V, packed19 ? 1 : 0, list, count, n_pts, d_rgb, d_views,  \
-                                                     surf_mlp_mode() == 4 ? 1 : 0)
+                                                     fast ? 1 : 0)
   switch (V) {
     case 2: BT_LAUNCH(2); break;
     case 3: BT_LAUNCH(3); break;

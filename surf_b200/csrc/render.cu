@@ -244,12 +244,12 @@ static int render_core_impl(const surf_scene* s, const surf_net* n, const surf_r
   src.list = w.list;
   src.count = w.counter;
   src.n = P;
-  rc = launch_sdf_mlp(s, n, src, out->d_sdf, out->d_gradients, false, st);
+  rc = launch_sdf_mlp(s, n, src, out->d_sdf, out->d_gradients, false, cfg->mlp_mode, st);
   if (rc) return rc;
   if (s->dev.V > 0) {
     rc = launch_lookup_feature(s, src, w.feat, w.rdiff, nullptr, false, st);
     if (rc) return rc;
-    rc = launch_blend(s, n, w.feat, w.rdiff, nullptr, s->dev.V, false, w.list, w.counter, P, color, views, st);
+    rc = launch_blend(s, n, w.feat, w.rdiff, nullptr, s->dev.V, false, w.list, w.counter, P, color, views, cfg->mlp_mode, st);
     if (rc) return rc;
   }
   const float sample_dist = 2.0f / (float)cfg->n_samples[0];

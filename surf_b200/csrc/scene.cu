@@ -21,14 +21,37 @@ void surf_set_error(const char* fmt, ...) {
 }
 void surf_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+// SM count of the CURRENT device (cached per device ordinal; a process may drive several GPUs)
 int surf_num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  static std::atomic<int> cache[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (dev >= 0 && dev < 64) {
+    const int c = cache[dev].load(std::memory_order_relaxed);
+    if (c > 0) return c;
   }
+  int n = 0;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  if (dev >= 0 && dev < 64) cache[dev].store(n, std::memory_order_relaxed);
   return n;
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute: set it once per (device, kernel),
+// thread-safe (launchers may be called from several host threads / for several devices).
+#include <mutex>
+#include <set>
+#include <utility>
+int surf_ensure_dyn_smem(const void* func, int bytes) {
+  static std::mutex mu;
+  static std::set<std::pair<int, const void*>> done;
+  int dev = 0;
+  SURF_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(mu);
+  const auto key = std::make_pair(dev, func);
+  if (done.count(key)) return 0;
+  SURF_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  done.insert(key);
+  return 0;
 }
 
 // ---- optional kernel timing -------------------------------------------------------------------
@@ -174,6 +197,8 @@ static int scene_alloc(surf_scene* s, void** p, size_t bytes) {
 extern "C" void surf_scene_destroy(surf_scene* s) {
   if (!s) return;
   for (int i = 0; i < s->n_owned; ++i) cudaFree(s->owned[i]);
+  for (int i = 0; i < 4; ++i)
+    if (s->view_buf[i]) cudaFree(s->view_buf[i]);
   delete s;
 }
 
@@ -198,6 +223,63 @@ extern "C" int surf_scene_update_volume(surf_scene* s, int32_t level, const floa
   SURF_CHECK_ARG(level >= 0 && level < s->dev.n_levels, "level out of range");
   SURF_CHECK_ARG(n_vox == s->nvox[level], "voxel count changed");
   return pad_volume(s, level, d_volume, n_vox, (cudaStream_t)stream);
+}
+
+// Per-batch part of a scene: source images / feature maps (NHWC re-layout) and cameras.  May be called any number
+// of times on a live scene (SuRF.forward selects `view_ids` per step, surf.py:140-146): buffers are reused when the
+// shape is unchanged, everything is stream-ordered on `stream`.
+extern "C" int surf_scene_set_views(surf_scene* s, const surf_scene_views* in, void* stream) {
+  SURF_CHECK_ARG(s && in, "scene/views null");
+  SURF_CHECK_ARG(in->n_views >= 1 && in->n_views - 1 <= SURF_MAX_VIEWS, "n_views out of range");
+  SURF_CHECK_ARG(in->h_intrs && in->h_w2cs && in->h_c2ws, "camera matrices missing");
+  cudaStream_t st = (cudaStream_t)stream;
+  DevScene& d = s->dev;
+  d.nv = in->n_views;
+  d.V = in->n_views - 1;
+  if (in->d_imgs) {
+    SURF_CHECK_ARG(in->n_feat_levels == 4, "4 feature pyramid levels expected");
+    SURF_CHECK_ARG(in->img_h >= 8 && in->img_w >= 8, "image too small");
+    for (int i = 0; i < 4; ++i) SURF_CHECK_ARG(in->d_features[i] != nullptr, "feature level null");
+    d.H = in->img_h;
+    d.W = in->img_w;
+    s->stats.bytes_images = 0;
+    for (int i = 0; i < 4; ++i) {
+      d.fh[i] = in->img_h >> i;
+      d.fw[i] = in->img_w >> i;
+      const size_t ni = (size_t)d.nv * d.fh[i] * d.fw[i];
+      const size_t bytes = ni * (i == 0 ? 32 : 16);
+      if (s->view_bytes[i] != bytes) {
+        if (s->view_buf[i]) SURF_CUDA(cudaFreeAsync(s->view_buf[i], st));
+        s->view_buf[i] = nullptr;
+        s->view_bytes[i] = 0;
+        SURF_CUDA(cudaMallocAsync(&s->view_buf[i], bytes, st));
+        s->view_bytes[i] = bytes;
+      }
+      if (i == 0) {
+        d.img0 = (const float4*)s->view_buf[0];
+        k_img0_nhwc<<<grid_for(ni, 256), 256, 0, st>>>(in->d_imgs, in->d_features[0], (float4*)s->view_buf[0], d.nv, d.H, d.W);
+      } else {
+        d.feat[i] = (const float4*)s->view_buf[i];
+        k_feat_nhwc<<<grid_for(ni, 256), 256, 0, st>>>(in->d_features[i], (float4*)s->view_buf[i], d.nv, d.fh[i], d.fw[i]);
+      }
+      SURF_LAUNCH_CHECK();
+      s->stats.bytes_images += bytes;
+    }
+  }
+  for (int v = 0; v < d.V; ++v) {
+    const float* w = in->h_w2cs + (size_t)(v + 1) * 16;
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 4; ++c) d.w2c[v][r * 4 + c] = w[r * 4 + c];
+    const float* k = in->h_intrs + (size_t)(v + 1) * 16;
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) d.K[v][r * 3 + c] = k[r * 4 + c];
+    const float* c2w = in->h_c2ws + (size_t)(v + 1) * 16;
+    for (int r = 0; r < 3; ++r) d.cen[v][r] = c2w[r * 4 + 3];
+  }
+  for (int r = 0; r < 3; ++r) d.refcen[r] = in->h_c2ws[r * 4 + 3];
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) d.rot0inv[r * 3 + c] = in->h_w2cs[r * 4 + c];
+  return 0;
 }
 
 extern "C" int surf_scene_create(const surf_scene_inputs* in, void* stream, surf_scene** out) {
@@ -294,55 +376,19 @@ extern "C" int surf_scene_create(const surf_scene_inputs* in, void* stream, surf
     s->stats.bytes_matching = n3 * sizeof(float);
   }
 
-  d.nv = in->n_views;
-  d.V = in->n_views > 0 ? in->n_views - 1 : 0;
-  d.H = in->img_h;
-  d.W = in->img_w;
-  if (in->d_imgs) {
-    if (in->n_feat_levels != 4 || !in->h_intrs || !in->h_w2cs || !in->h_c2ws) {
-      surf_set_error("images given but n_feat_levels != 4 or camera matrices missing");
-      surf_scene_destroy(s);
-      return -1;
-    }
-    for (int i = 0; i < 4; ++i) {
-      if (!in->d_features[i]) {
-        surf_set_error("feature level %d null", i);
-        surf_scene_destroy(s);
-        return -1;
-      }
-      d.fh[i] = in->img_h >> i;
-      d.fw[i] = in->img_w >> i;
-    }
-    void* p = nullptr;
-    const size_t n0 = (size_t)d.nv * d.H * d.W;
-    SC_TRY(scene_alloc(s, &p, n0 * 32));
-    d.img0 = (const float4*)p;
-    k_img0_nhwc<<<grid_for(n0, 256), 256, 0, st>>>(in->d_imgs, in->d_features[0], (float4*)p, d.nv, d.H, d.W);
-    surf_count_launch();
-    s->stats.bytes_images += n0 * 32;
-    for (int i = 1; i < 4; ++i) {
-      const size_t ni = (size_t)d.nv * d.fh[i] * d.fw[i];
-      SC_TRY(scene_alloc(s, &p, ni * 16));
-      d.feat[i] = (const float4*)p;
-      k_feat_nhwc<<<grid_for(ni, 256), 256, 0, st>>>(in->d_features[i], (float4*)p, d.nv, d.fh[i], d.fw[i]);
-      surf_count_launch();
-      s->stats.bytes_images += ni * 16;
-    }
-  }
-  if (in->h_w2cs && in->h_c2ws && in->h_intrs) {
-    for (int v = 0; v < d.V; ++v) {
-      const float* w = in->h_w2cs + (size_t)(v + 1) * 16;
-      for (int r = 0; r < 3; ++r)
-        for (int c = 0; c < 4; ++c) d.w2c[v][r * 4 + c] = w[r * 4 + c];
-      const float* k = in->h_intrs + (size_t)(v + 1) * 16;
-      for (int r = 0; r < 3; ++r)
-        for (int c = 0; c < 3; ++c) d.K[v][r * 3 + c] = k[r * 4 + c];
-      const float* c2w = in->h_c2ws + (size_t)(v + 1) * 16;
-      for (int r = 0; r < 3; ++r) d.cen[v][r] = c2w[r * 4 + 3];
-    }
-    for (int r = 0; r < 3; ++r) d.refcen[r] = in->h_c2ws[r * 4 + 3];
-    for (int r = 0; r < 3; ++r)
-      for (int c = 0; c < 3; ++c) d.rot0inv[r * 3 + c] = in->h_w2cs[r * 4 + c];
+  if (in->n_views > 0) {
+    surf_scene_views v;
+    memset(&v, 0, sizeof(v));
+    v.n_views = in->n_views;
+    v.img_h = in->img_h;
+    v.img_w = in->img_w;
+    v.n_feat_levels = in->n_feat_levels;
+    v.d_imgs = in->d_imgs;
+    for (int i = 0; i < 4; ++i) v.d_features[i] = in->d_features[i];
+    v.h_intrs = in->h_intrs;
+    v.h_w2cs = in->h_w2cs;
+    v.h_c2ws = in->h_c2ws;
+    SC_TRY(surf_scene_set_views(s, &v, stream));
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {

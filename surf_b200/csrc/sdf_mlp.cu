@@ -439,17 +439,6 @@ static inline int perm_pos_128(int n) {   // column n -> position inside a permu
 int surf_build_tc_weights(const std::vector<std::vector<float>>& W, const surf_net_inputs* in, surf_net* net,
                           cudaStream_t st, int (*dev_alloc)(surf_net*, void**, size_t));
 
-int surf_build_tc1_weights(const std::vector<std::vector<float>>& W, const surf_net_inputs* in, surf_net* net,
-                           cudaStream_t st, int (*dev_alloc)(surf_net*, void**, size_t));
-
-static int g_mlp_mode = 0;
-int surf_mlp_mode() { return g_mlp_mode; }
-extern "C" int surf_set_mlp_mode(int32_t mode) {
-  SURF_CHECK_ARG(mode >= 0 && mode <= 5, "mlp mode must be 0..5");
-  g_mlp_mode = mode;
-  return 0;
-}
-
 int surf_build_sdf_weights(const surf_net_inputs* in, surf_net* net, cudaStream_t st,
                            int (*dev_alloc)(surf_net*, void**, size_t)) {
   SURF_CHECK_ARG(in->n_lin == SURF_SDF_LAYERS, "n_lin must be 7");
@@ -562,8 +551,6 @@ int surf_build_sdf_weights(const surf_net_inputs* in, surf_net* net, cudaStream_
   if (net->tc_ok) {
     rc = surf_build_tc_weights(W, in, net, st, dev_alloc);
     if (rc) return rc;
-    rc = surf_build_tc1_weights(W, in, net, st, dev_alloc);
-    if (rc) return rc;
   }
   net->dev.b6 = in->h_bias[6][0];
   net->dev.scale = in->scale;
@@ -577,25 +564,15 @@ int surf_build_sdf_weights(const surf_net_inputs* in, surf_net* net, cudaStream_
 }
 
 int launch_sdf_mlp(const surf_scene* s, const surf_net* n, const PointSource& src, float* d_sdf, float* d_grad,
-                   bool negate, cudaStream_t st) {
-  static bool attr_set = false;
-  const size_t smem = SM_TOTAL * sizeof(float);
-  if (!attr_set) {
-    SURF_CUDA(cudaFuncSetAttribute(k_sdf_mlp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    SURF_CUDA(cudaFuncSetAttribute(k_sdf_mlp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+                   bool negate, int mode, cudaStream_t st) {
   if (src.n <= 0) return 0;
-  if (g_mlp_mode >= 1 && n->tc_ok) {
-    // modes 1 / 4: the pipelined one-tile kernel (sdf_tc2.cu); modes 2 / 3: the first-generation kernels, kept for
-    // comparison (sdf_tc.cu: two forward tile pipelines; sdf_tc1.cu: forward + gradient, layer-serial)
-    if (g_mlp_mode == 2 || g_mlp_mode == 3) {
-      if (d_grad) return launch_sdf_tc1(s, n, src, d_sdf, d_grad, negate, st);
-      return launch_sdf_tc_fwd(s, n, src, d_sdf, negate, st);
-    }
-    if (g_mlp_mode == 5) return launch_sdf_tc3(s, n, src, d_sdf, d_grad, negate, st);
-    return launch_sdf_tc2(s, n, src, d_sdf, d_grad, negate, st);
-  }
+  SURF_CHECK_ARG(mode == SURF_MLP_FFMA || mode == SURF_MLP_TC || mode == SURF_MLP_TC_FAST, "mlp_mode must be SURF_MLP_FFMA, SURF_MLP_TC or SURF_MLP_TC_FAST");
+  if (mode != SURF_MLP_FFMA && n->tc_ok) return launch_sdf_tc2(s, n, src, d_sdf, d_grad, negate, mode == SURF_MLP_TC_FAST, st);
+  const size_t smem = SM_TOTAL * sizeof(float);
+  int rc = surf_ensure_dyn_smem((const void*)k_sdf_mlp<true>, (int)smem);
+  if (rc) return rc;
+  rc = surf_ensure_dyn_smem((const void*)k_sdf_mlp<false>, (int)smem);
+  if (rc) return rc;
   int64_t tiles = (src.n + MLP_TILE - 1) / MLP_TILE;
   int grid = (int)(tiles < n->n_sm ? tiles : n->n_sm);
   surf_time_begin(d_grad ? 0 : 1, st);
@@ -610,7 +587,7 @@ int launch_sdf_mlp(const surf_scene* s, const surf_net* n, const PointSource& sr
 }
 
 extern "C" int surf_sdf_points(const surf_scene* s, const surf_net* n, const float* d_pts, int64_t n_pts,
-                               float* d_sdf, float* d_grad, void* stream) {
+                               float* d_sdf, float* d_grad, int32_t mlp_mode, void* stream) {
   if (n_pts <= 0) return 0;
   SURF_CHECK_ARG(s && n && d_pts && d_sdf, "null pointer");
   SURF_CHECK_ARG(n_pts < 0x7fffffffll, "too many points for one call");
@@ -619,12 +596,12 @@ extern "C" int surf_sdf_points(const surf_scene* s, const surf_net* n, const flo
   src.mode = 0;
   src.pts = d_pts;
   src.n = n_pts;
-  return launch_sdf_mlp(s, n, src, d_sdf, d_grad, false, (cudaStream_t)stream);
+  return launch_sdf_mlp(s, n, src, d_sdf, d_grad, false, mlp_mode, (cudaStream_t)stream);
 }
 
 extern "C" int surf_sdf_grid(const surf_scene* s, const surf_net* n, const float* d_xs, int32_t nx, const float* d_ys,
                              int32_t ny, const float* d_zs, int32_t nz, float* d_u, int32_t sparsify, float fill,
-                             void* stream) {
+                             int32_t mlp_mode, void* stream) {
   SURF_CHECK_ARG(s && n && d_xs && d_ys && d_zs && d_u, "null pointer");
   SURF_CHECK_ARG(nx > 0 && ny > 0 && nz > 0, "empty grid");
   const int64_t total = (int64_t)nx * ny * nz;
@@ -649,7 +626,7 @@ extern "C" int surf_sdf_grid(const surf_scene* s, const surf_net* n, const float
     src.list = list;
     src.count = counter;
   }
-  int rc = launch_sdf_mlp(s, n, src, d_u, nullptr, true, st);
+  int rc = launch_sdf_mlp(s, n, src, d_u, nullptr, true, mlp_mode, st);
   if (list) cudaFreeAsync(list, st);
   return rc;
 }

@@ -19,8 +19,9 @@
 // One thread issues every MMA, in a fixed order, into one accumulator per layer: results are bitwise deterministic.
 // Weight stream, hi/lo fp16 split (3 MMAs per product), u-code scratch for softplus': as sdf_tc1.cu.
 #include <math.h>
-#include <stdlib.h>
 #include <string.h>
+
+#include <vector>
 
 #include "surf_internal.cuh"
 #include "tc_common.cuh"
@@ -31,6 +32,7 @@
 #define T2_THREADS ((T2_EPI_WARPS + 2 + T2_HELP_WARPS) * 32)     // + 1 MMA issuer + 1 weight loader + helpers
 #define T2_SLOT_BYTES 20480                      // N = 160 x K = 32 x (hi + lo)
 #define T2_NSLOT 5
+#define T2_SCRATCH_U4 (5 * 4 * T2_EPI_THREADS + 5 * T2_EPI_THREADS / 4)   // per-CTA scratch, in uint4
 
 #define T2_D0 0u
 #define T2_D1 160u
@@ -413,7 +415,7 @@ k_sdf_tc2(const DevScene sc, const DevNet net, const PointSource src, const uint
     const int r = q * 32 + lane;                 // row = point = TMEM lane
     const uint32_t tl = tbase + ((uint32_t)(q * 32) << 16);
     float* s_part = reinterpret_cast<float*>(smem + S2_PART);
-    uint4* scratch = scratch_all + (size_t)blockIdx.x * (5 * 4 * T2_EPI_THREADS + 5 * T2_EPI_THREADS / 4);
+    uint4* scratch = scratch_all + (size_t)blockIdx.x * T2_SCRATCH_U4;
     uint32_t* sgn_scratch = reinterpret_cast<uint32_t*>(scratch + 5 * 4 * T2_EPI_THREADS);
     const int te = warp * 32 + lane;             // 0..511
     uint32_t ph_d = 0;
@@ -791,45 +793,129 @@ k_sdf_tc2(const DevScene sc, const DevNet net, const PointSource src, const uint
   if (warp == T2_EPI_WARPS) tc::tmem_dealloc<512>(tbase);
 }
 
-// the weight stream of sdf_tc1.cu with the feature | bias half chunks of every forward layer moved to the front
-static T1Stream t2_reordered_stream() {
-  T1Stream S = g_t1_stream;
+// ---------------------------------------------------------------------------------------------
+// host: the fp16 hi|lo weight stream, in the order the issuer consumes it
+//   forward : lin0 (K = 27 + bias column), then per layer lin1..lin5 the two K = 16 feature | bias half chunks
+//             (independent of the previous layer, issued first) followed by the four K = 32 hidden chunks;
+//   reverse : lin5..lin1 as B[n = input index (160 rows)][k = output index], four K = 32 chunks each; lin0 as
+//             B[n = PE index (32 rows)][k], two K = 64 chunks.
+// Chunk image = the K-major no-swizzle canonical smem layout: element (n, kk) at (kk >> 3) * rows * 8 + n * 8 + (kk & 7),
+// hi half first, lo half after it.
+// ---------------------------------------------------------------------------------------------
+static inline uint16_t t2_f2h(float f) {
+  __half h = __float2half_rn(f);
+  uint16_t b;
+  memcpy(&b, &h, 2);
+  return b;
+}
+static inline float t2_h2f(uint16_t b) {
+  __half h;
+  memcpy(&h, &b, 2);
+  return __half2float(h);
+}
+
+int surf_build_tc_weights(const std::vector<std::vector<float>>& W, const surf_net_inputs* in, surf_net* net,
+                          cudaStream_t st, int (*dev_alloc)(surf_net*, void**, size_t)) {
+  T1Stream& S = net->tc_stream;
+  memset(&S, 0, sizeof(S));
+  std::vector<uint16_t> blob;
+  int nc = 0;
+  auto add_chunk = [&](int rows, int K) {
+    const size_t half = (size_t)rows * K;           // halves
+    S.off[nc] = (uint32_t)(blob.size() * 2);
+    S.bytes[nc] = (uint32_t)(half * 2 * 2);
+    blob.resize(blob.size() + half * 2, 0);
+    return blob.size() - half * 2;
+  };
+  auto put = [&](size_t base, int rows, int K, int n, int kk, float v) {
+    const uint16_t hi = t2_f2h(v);
+    const uint16_t lo = t2_f2h(v - t2_h2f(hi));
+    const size_t off = (size_t)(kk >> 3) * rows * 8 + (size_t)n * 8 + (kk & 7);
+    blob[base + off] = hi;
+    blob[base + (size_t)rows * K + off] = lo;
+  };
+  {
+    const int O = in->out_dim[0], I = in->in_dim[0];
+    const size_t b = add_chunk(128, 32);
+    for (int n = 0; n < O && n < 128; ++n) {
+      for (int k = 0; k < I; ++k) put(b, 128, 32, n, k, W[0][(size_t)n * I + k]);
+      put(b, 128, 32, n, 27, in->h_bias[0][n]);
+    }
+    nc++;
+  }
   for (int l = 1; l < 6; ++l) {
-    const int base = 1 + (l - 1) * 6;
-    const int order[6] = {4, 5, 0, 1, 2, 3};
-    for (int c = 0; c < 6; ++c) {
-      S.off[base + c] = g_t1_stream.off[base + order[c]];
-      S.bytes[base + c] = g_t1_stream.bytes[base + order[c]];
+    const int O = in->out_dim[l], I = in->in_dim[l];
+    const int order[6] = {4, 5, 0, 1, 2, 3};        // feature | bias halves first
+    for (int ci = 0; ci < 6; ++ci) {
+      const int c = order[ci];
+      const int K = c < 4 ? 32 : 16;
+      const int kbase = c < 4 ? c * 32 : 128 + (c - 4) * 16;
+      const size_t b = add_chunk(128, K);
+      for (int n = 0; n < O && n < 128; ++n)
+        for (int kk = 0; kk < K; ++kk) {
+          const int k = kbase + kk;
+          if (k < I) put(b, 128, K, n, kk, W[l][(size_t)n * I + k]);
+          else if (k == 156) put(b, 128, K, n, kk, in->h_bias[l][n]);
+        }
+      nc++;
     }
   }
-  return S;
+  S.n_fwd = nc;
+  for (int l = 5; l >= 1; --l) {
+    const int O = in->out_dim[l], I = in->in_dim[l];
+    for (int c = 0; c < 4; ++c) {
+      const size_t b = add_chunk(160, 32);
+      for (int kk = 0; kk < 32; ++kk) {
+        const int k = c * 32 + kk;
+        if (k >= O) continue;
+        for (int n = 0; n < I && n < 160; ++n) put(b, 160, 32, n, kk, W[l][(size_t)k * I + n]);
+      }
+      nc++;
+    }
+  }
+  {
+    const int O = in->out_dim[0], I = in->in_dim[0];
+    for (int c = 0; c < 2; ++c) {
+      const size_t b = add_chunk(32, 64);
+      for (int kk = 0; kk < 64; ++kk) {
+        const int k = c * 64 + kk;
+        if (k >= O) continue;
+        for (int n = 0; n < I && n < 32; ++n) put(b, 32, 64, n, kk, W[0][(size_t)k * I + n]);
+      }
+      nc++;
+    }
+  }
+  S.n_all = nc;
+  void* p = nullptr;
+  int rc = dev_alloc(net, &p, blob.size() * 2);
+  if (rc) return rc;
+  SURF_CUDA(cudaMemcpyAsync(p, blob.data(), blob.size() * 2, cudaMemcpyHostToDevice, st));
+  SURF_CUDA(cudaStreamSynchronize(st));
+  net->tc_blob = (const uint8_t*)p;
+  // softplus' code scratch: per CTA 5 layers x 4 groups x 512 threads x 16 B (+ the sign words)
+  rc = dev_alloc(net, &p, (size_t)net->n_sm * T2_SCRATCH_U4 * sizeof(uint4));
+  if (rc) return rc;
+  net->tc_scratch = p;
+  return 0;
 }
 
 int launch_sdf_tc2(const surf_scene* s, const surf_net* n, const PointSource& src, float* d_sdf, float* d_grad,
-                   bool negate, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    SURF_CUDA(cudaFuncSetAttribute(k_sdf_tc2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, S2_TOTAL + T2_TRACE_SMEM));
-    SURF_CUDA(cudaFuncSetAttribute(k_sdf_tc2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, S2_TOTAL + T2_TRACE_SMEM));
-    attr_set = true;
-  }
+                   bool negate, bool fast, cudaStream_t st) {
   if (src.n <= 0) return 0;
-  const T1Stream stream = t2_reordered_stream();
+  int rc = surf_ensure_dyn_smem((const void*)k_sdf_tc2<true>, S2_TOTAL + T2_TRACE_SMEM);
+  if (rc) return rc;
+  rc = surf_ensure_dyn_smem((const void*)k_sdf_tc2<false>, S2_TOTAL + T2_TRACE_SMEM);
+  if (rc) return rc;
   const int64_t tiles = (src.n + 127) / 128;
   const int grid = (int)(tiles < n->n_sm ? tiles : n->n_sm);
-  static int dbg = -1;
-  if (dbg < 0) {
-    const char* e = getenv("SURF_T2_DEBUG");
-    dbg = e ? atoi(e) : 0;
-  }
-  const int flags = (negate ? 1 : 0) | (surf_mlp_mode() == 4 ? 2 : 0) | dbg;
+  const int flags = (negate ? 1 : 0) | (fast ? 2 : 0);
   surf_time_begin(d_grad ? 0 : 1, st);
   if (d_grad) {
-    k_sdf_tc2<true><<<grid, T2_THREADS, S2_TOTAL + T2_TRACE_SMEM, st>>>(s->dev, n->dev, src, n->tc1_blob, stream, d_sdf, d_grad,
-                                                                        (uint4*)n->tc1_scratch, flags);
+    k_sdf_tc2<true><<<grid, T2_THREADS, S2_TOTAL + T2_TRACE_SMEM, st>>>(s->dev, n->dev, src, n->tc_blob, n->tc_stream, d_sdf,
+                                                                        d_grad, (uint4*)n->tc_scratch, flags);
   } else {
-    k_sdf_tc2<false><<<grid, T2_THREADS, S2_TOTAL + T2_TRACE_SMEM, st>>>(s->dev, n->dev, src, n->tc1_blob, stream, d_sdf, nullptr,
-                                                                         (uint4*)n->tc1_scratch, flags);
+    k_sdf_tc2<false><<<grid, T2_THREADS, S2_TOTAL + T2_TRACE_SMEM, st>>>(s->dev, n->dev, src, n->tc_blob, n->tc_stream, d_sdf,
+                                                                         nullptr, (uint4*)n->tc_scratch, flags);
   }
   surf_time_end(d_grad ? 0 : 1, st);
   SURF_LAUNCH_CHECK();

@@ -35,6 +35,8 @@ struct surf_scene {
   DevScene dev;
   void* owned[64];
   int n_owned;
+  void* view_buf[4];                      // NHWC image / feature maps of the current views (surf_scene_set_views)
+  size_t view_bytes[4];
   surf_scene_stats stats;
   int64_t nvox[SURF_MAX_LEVELS];
 };
@@ -74,17 +76,26 @@ struct DevNet {
   MlpStream stream;
 };
 
+// weight stream of the tensor-core SDF kernel (sdf_tc2.cu): byte offsets / sizes of the fp16 hi|lo chunks
+#define T1_MAXCHUNK 64
+struct T1Stream {
+  int n_fwd, n_all;
+  uint32_t off[T1_MAXCHUNK];      // byte offset in the blob
+  uint32_t bytes[T1_MAXCHUNK];
+};
+
 struct surf_net {
   DevNet dev;
   void* owned[16];
   int n_owned;
-  const uint8_t* tc_blob;           // tensor-core weight stream (fp16 hi/lo chunks, sdf_tc.cu)
-  const uint8_t* tc1_blob;          // forward + reverse weight stream of sdf_tc1.cu
-  void* tc1_scratch;                // softplus' scratch (unorm16) of sdf_tc1.cu
+  const uint8_t* tc_blob;           // tensor-core weight stream (fp16 hi/lo chunks, forward then reverse)
+  T1Stream tc_stream;               // chunk table of tc_blob in the order sdf_tc2.cu consumes it
+  void* tc_scratch;                 // softplus' code scratch of sdf_tc2.cu (per-CTA private, L2-resident)
   const uint8_t* blend_tc_w;        // blend_tc.cu: fp16 hi/lo tensor-core operands
   const float* blend_tc_f;          // blend_tc.cu: fp32 small-layer weights and biases
+  const float* w6_full;             // (out6, 160) folded lin6 rows + bias (opt-in full (n,129) head)
   int tc_ok;                        // network shape supported by the tensor-core kernels
-  float* scratch;                   // sigma' scratch for the backward pass (per-CTA private)
+  float* scratch;                   // sigma' scratch of the FFMA backward pass (per-CTA private)
   size_t scratch_bytes;
   int n_sm;
 };
@@ -98,6 +109,7 @@ void surf_time_begin(int kind, cudaStream_t st);
 void surf_time_end(int kind, cudaStream_t st);
 void surf_count_launch(int n = 1);
 int surf_num_sms();
+int surf_ensure_dyn_smem(const void* func, int bytes);   // per (device, kernel), thread-safe
 
 #define SURF_CHECK_ARG(cond, msg)            \
   do {                                       \
@@ -278,30 +290,16 @@ struct PointSource {
   int sparsify; float fill;
 };
 
+// mode: SURF_MLP_* (include/surf_b200.h); the tensor-core editions are used when mode != SURF_MLP_FFMA and n->tc_ok
 int launch_sdf_mlp(const surf_scene* s, const surf_net* n, const PointSource& src, float* d_sdf, float* d_grad,
-                   bool negate, cudaStream_t st);
-int launch_sdf_tc_fwd(const surf_scene* s, const surf_net* n, const PointSource& src, float* d_sdf, bool negate,
-                      cudaStream_t st);
-// weight stream of the tensor-core forward + reverse kernels (sdf_tc1.cu builds it, sdf_tc2.cu re-orders it)
-#define T1_MAXCHUNK 64
-struct T1Stream {
-  int n_fwd, n_all;
-  uint32_t off[T1_MAXCHUNK];      // byte offset in the blob
-  uint32_t bytes[T1_MAXCHUNK];
-};
-extern T1Stream g_t1_stream;
-int launch_sdf_tc3(const surf_scene* s, const surf_net* n, const PointSource& src, float* d_sdf, float* d_grad,
-                   bool negate, cudaStream_t st);
+                   bool negate, int mode, cudaStream_t st);
 int launch_sdf_tc2(const surf_scene* s, const surf_net* n, const PointSource& src, float* d_sdf, float* d_grad,
-                   bool negate, cudaStream_t st);
-int launch_sdf_tc1(const surf_scene* s, const surf_net* n, const PointSource& src, float* d_sdf, float* d_grad,
-                   bool negate, cudaStream_t st);
+                   bool negate, bool fast, cudaStream_t st);
 int launch_blend_tc(const surf_net* n, const float* d_feat, const float* d_raydiff, const uint8_t* d_mask, int V,
                     bool packed19, const int32_t* list, const int32_t* count, int64_t n_pts, float* d_rgb,
-                    uint8_t* d_views, cudaStream_t st);
-int surf_mlp_mode();   // 0 = fp32 FFMA kernels, 1 = tcgen05 kernels (fp16 hi/lo split, fp32-grade)
+                    uint8_t* d_views, bool fast, cudaStream_t st);
 int launch_lookup_feature(const surf_scene* s, const PointSource& src, float* d_feat, float* d_raydiff,
                           uint8_t* d_mask, bool packed19, cudaStream_t st);
 int launch_blend(const surf_scene* s_or_null, const surf_net* n, const float* d_feat, const float* d_raydiff,
                  const uint8_t* d_mask_or_null, int V, bool packed19, const int32_t* list, const int32_t* count,
-                 int64_t n_pts, float* d_rgb, uint8_t* d_views, cudaStream_t st);
+                 int64_t n_pts, float* d_rgb, uint8_t* d_views, int mode, cudaStream_t st);

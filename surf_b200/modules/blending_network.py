@@ -60,7 +60,8 @@ class BlendingNetwork(nn.Module):
         """rgb_feat (n,V,19), ray_diff (n,V,4), mask (n,V) bool -> rgb (n,3)."""
         if self._net_owner is None:
             raise RuntimeError("BlendingNetwork must be owned by an ImplicitSurface to build its device weights")
-        net = self._net_owner().net_handle()
+        owner = self._net_owner()
+        net = owner.net_handle()
         n, V, c = rgb_feat.shape
         if c != self.d_feature + 3:
             raise ValueError("expected %d channels" % (self.d_feature + 3))
@@ -68,6 +69,8 @@ class BlendingNetwork(nn.Module):
         r = ray_diff.detach().to(torch.float32).contiguous()
         m = mask.detach().to(torch.uint8).contiguous()
         out = torch.empty((n, 3), dtype=torch.float32, device=f.device)
-        _lib.check(_lib.load().surf_blend(net, f.data_ptr(), r.data_ptr(), m.data_ptr(), n, V, out.data_ptr(),
-                                          C.c_void_p(torch.cuda.current_stream().cuda_stream)), "blend")
+        with torch.cuda.device(f.device):
+            _lib.check(_lib.load().surf_blend(net, f.data_ptr(), r.data_ptr(), m.data_ptr(), n, V, out.data_ptr(),
+                                              int(owner.mlp_mode),
+                                              C.c_void_p(torch.cuda.current_stream().cuda_stream)), "blend")
         return out

@@ -64,6 +64,14 @@ class ImplicitSurface(nn.Module):
         self._ws = None
         self.scene_cache = GLOBAL_SCENE_CACHE
         self.ray_batch = 1 << 16        # rays per launch set in validate()
+        # MLP kernel family of every call made through this module (include/surf_b200.h SURF_MLP_*): the tcgen05
+        # fp32-grade kernels by default; optional conf key ``mlp_mode`` (not a reference key) or assign the attribute
+        mode = _lib.MLP_TC
+        try:
+            mode = confs.get_int("mlp_mode", default=_lib.MLP_TC)
+        except Exception:
+            pass
+        self.mlp_mode = int(mode)
 
     # -- device handles --------------------------------------------------------------------------
     def net_handle(self):
@@ -105,7 +113,9 @@ class ImplicitSurface(nn.Module):
         cfg.cos_anneal_ratio = float(cos_anneal_ratio)
         cfg.chunk_rays = int(chunk_rays)
         cfg.d_lin_tables = self._lin_tables(device).data_ptr()
-        cfg.mlp_mode = 0
+        if self.mlp_mode not in _lib.MLP_MODES:
+            raise ValueError("mlp_mode must be one of %s" % (_lib.MLP_MODES,))
+        cfg.mlp_mode = int(self.mlp_mode)
         return cfg
 
     def _workspace(self, device, B, S, V):
@@ -174,14 +184,17 @@ class ImplicitSurface(nn.Module):
             tr = None
             if t_rand is not None and self.perturb > 0:
                 tr = t_rand.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
-            _lib.check(lib.surf_render_rays(scene.handle, net, C.byref(cfg), rays_o.data_ptr(), rays_d.data_ptr(),
-                                            near.data_ptr(), far.data_ptr(), tr.data_ptr() if tr is not None else None,
-                                            B, C.byref(o), ws.data_ptr(), ws.numel(), _stream()), "render_rays")
+            with torch.cuda.device(dev):
+                _lib.check(lib.surf_render_rays(scene.handle, net, C.byref(cfg), rays_o.data_ptr(), rays_d.data_ptr(),
+                                                near.data_ptr(), far.data_ptr(),
+                                                tr.data_ptr() if tr is not None else None, B, C.byref(o), ws.data_ptr(),
+                                                ws.numel(), _stream()), "render_rays")
         else:
             z = z_vals.detach().to(torch.float32).contiguous()
-            _lib.check(lib.surf_render_core(scene.handle, net, C.byref(cfg), rays_o.data_ptr(), rays_d.data_ptr(),
-                                            z.data_ptr(), B, S, C.byref(o), ws.data_ptr(), ws.numel(), _stream()),
-                       "render_core")
+            with torch.cuda.device(dev):
+                _lib.check(lib.surf_render_core(scene.handle, net, C.byref(cfg), rays_o.data_ptr(), rays_d.data_ptr(),
+                                                z.data_ptr(), B, S, C.byref(o), ws.data_ptr(), ws.numel(), _stream()),
+                           "render_core")
         return t
 
     def sample_z(self, scene, rays_o, rays_d, near, far, t_rand):
@@ -197,9 +210,10 @@ class ImplicitSurface(nn.Module):
         near = near.detach().float().contiguous()
         far = far.detach().float().contiguous()
         tr = t_rand.to(device=dev, dtype=torch.float32).contiguous() if (t_rand is not None and self.perturb > 0) else None
-        _lib.check(lib.surf_sample_rays(scene.handle, C.byref(cfg), rays_o.data_ptr(), rays_d.data_ptr(), near.data_ptr(),
-                                        far.data_ptr(), tr.data_ptr() if tr is not None else None, B, z.data_ptr(),
-                                        surf.data_ptr(), _stream()), "sample_rays")
+        with torch.cuda.device(dev):
+            _lib.check(lib.surf_sample_rays(scene.handle, C.byref(cfg), rays_o.data_ptr(), rays_d.data_ptr(),
+                                            near.data_ptr(), far.data_ptr(), tr.data_ptr() if tr is not None else None,
+                                            B, z.data_ptr(), surf.data_ptr(), _stream()), "sample_rays")
         return z, surf
 
     def _sparse_sdf_random(self, scene, pts_random, device):
@@ -207,11 +221,15 @@ class ImplicitSurface(nn.Module):
         lib = _lib.load()
         p = pts_random.to(device=device, dtype=torch.float32).contiguous()
         m = torch.empty(p.shape[0], dtype=torch.uint8, device=device)
-        _lib.check(lib.surf_point_mask(scene.handle, p.data_ptr(), p.shape[0], m.data_ptr(), _stream()), "point_mask")
         s = torch.empty((p.shape[0], 1), dtype=torch.float32, device=device)
-        _lib.check(lib.surf_sdf_points(scene.handle, self.net_handle(), p.data_ptr(), p.shape[0], s.data_ptr(), None,
-                                       _stream()), "sdf_points")
-        return s * m[:, None].to(torch.float32)
+        with torch.cuda.device(device):
+            _lib.check(lib.surf_point_mask(scene.handle, p.data_ptr(), p.shape[0], m.data_ptr(), _stream()),
+                       "point_mask")
+            _lib.check(lib.surf_sdf_points(scene.handle, self.net_handle(), p.data_ptr(), p.shape[0], s.data_ptr(),
+                                           None, int(self.mlp_mode), _stream()), "sdf_points")
+        # the reference scatters the masked points into zeros (:175-178): exactly 0 outside the mask, also where the
+        # extrapolating trilinear weights of a far-away point overflow (inf * 0 would be NaN)
+        return torch.where(m[:, None].bool(), s, torch.zeros_like(s))
 
     def _finish_dict(self, t, scene, B, S, pts_random, device):
         inv_s = self.deviation_network.inv_s().to(device)
@@ -294,11 +312,13 @@ class ImplicitSurface(nn.Module):
         net = self.net_handle()
         # keep every launch below 2^31 points
         max_planes = max(1, (2 ** 31 - 1) // (resolution * resolution))
-        for x0 in range(0, X.numel(), max_planes):
-            xs = X[x0:x0 + max_planes].contiguous()
-            _lib.check(lib.surf_sdf_grid(scene.handle, net, xs.data_ptr(), xs.numel(), Y.data_ptr(), resolution,
-                                         Z.data_ptr(), resolution, u[x0:x0 + xs.numel()].data_ptr(),
-                                         1 if sparsify else 0, float(fill), _stream()), "sdf_grid")
+        with torch.cuda.device(dev):
+            for x0 in range(0, X.numel(), max_planes):
+                xs = X[x0:x0 + max_planes].contiguous()
+                _lib.check(lib.surf_sdf_grid(scene.handle, net, xs.data_ptr(), xs.numel(), Y.data_ptr(), resolution,
+                                             Z.data_ptr(), resolution, u[x0:x0 + xs.numel()].data_ptr(),
+                                             1 if sparsify else 0, float(fill), int(self.mlp_mode), _stream()),
+                           "sdf_grid")
         return u
 
     def extract_geometry(self, volumes, sparse_idxes, bound_min, bound_max, resolution, threshold):
@@ -376,6 +396,10 @@ class ImplicitSurface(nn.Module):
             t_rand = t_rand.to(rays_o.device, non_blocking=True)
         step_rays = max(chunk, (self.ray_batch // chunk) * chunk)
         acc = {k: [] for k in ("color_fine", "val_normal", "sdf_depth", "render_depth")}
+        if n == 0:      # an empty shard (more ranks than 256-ray chunks): correctly shaped empty tensors
+            f32 = dict(dtype=torch.float32, device=rays_o.device)
+            return {"color_fine": torch.empty((0, 3), **f32), "val_normal": torch.empty((0, 3), **f32),
+                    "sdf_depth": torch.empty((0, 1), **f32), "render_depth": torch.empty((0,), **f32)}
         for r0 in range(0, n, step_rays):
             r1 = min(n, r0 + step_rays)
             tr = None if t_rand is None else t_rand[r0:r1]

@@ -14,7 +14,7 @@ import torch
 import torch.nn as nn
 
 from .. import _lib
-from ..scene import GLOBAL_SCENE_CACHE, PreparedScene
+from ..scene import AUX_SCENE_CACHE, PreparedScene
 from .embedder import embedder_out_dim
 
 
@@ -101,18 +101,20 @@ class SDFNetworkSparse(nn.Module):
     def _handles(self, volumes, indexes):
         if self._net_owner is None:
             raise RuntimeError("SDFNetworkSparse must be owned by an ImplicitSurface to build its device weights")
-        net = self._net_owner().net_handle()
-        scene = volumes if isinstance(volumes, PreparedScene) else GLOBAL_SCENE_CACHE.get(volumes, indexes)
-        return scene, net
+        owner = self._net_owner()
+        net = owner.net_handle()
+        scene = volumes if isinstance(volumes, PreparedScene) else AUX_SCENE_CACHE.get(volumes, indexes)
+        return scene, net, int(owner.mlp_mode)
 
     # -- reference API -------------------------------------------------------------------------
     def sdf(self, x, volumes, indexes=None):
         """(n,3) -> (n,1)   (sdf_network.py:123-124).  ``volumes`` may be a PreparedScene."""
-        scene, net = self._handles(volumes, indexes)
+        scene, net, mode = self._handles(volumes, indexes)
         x = x.detach().to(torch.float32).contiguous()
         out = torch.empty((x.shape[0], 1), dtype=torch.float32, device=x.device)
-        _lib.check(_lib.load().surf_sdf_points(scene.handle, net, x.data_ptr(), x.shape[0], out.data_ptr(), None,
-                                               _stream()), "sdf_points")
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().surf_sdf_points(scene.handle, net, x.data_ptr(), x.shape[0], out.data_ptr(), None,
+                                                   mode, _stream()), "sdf_points")
         return out
 
     def gradient(self, x, volumes, indexes=None, with_sdf=False):
@@ -120,12 +122,13 @@ class SDFNetworkSparse(nn.Module):
 
         The reference also returns the second-order ``smooth`` term (:143-150), a training-only extra
          that is not implemented; zeros are returned in its place."""
-        scene, net = self._handles(volumes, indexes)
+        scene, net, mode = self._handles(volumes, indexes)
         x = x.detach().to(torch.float32).contiguous()
         sdf = torch.empty((x.shape[0], 1), dtype=torch.float32, device=x.device)
         grad = torch.empty((x.shape[0], 3), dtype=torch.float32, device=x.device)
-        _lib.check(_lib.load().surf_sdf_points(scene.handle, net, x.data_ptr(), x.shape[0], sdf.data_ptr(),
-                                               grad.data_ptr(), _stream()), "sdf_points(grad)")
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().surf_sdf_points(scene.handle, net, x.data_ptr(), x.shape[0], sdf.data_ptr(),
+                                                   grad.data_ptr(), mode, _stream()), "sdf_points(grad)")
         if with_sdf:
             return sdf, grad
         return grad, torch.zeros_like(grad)
