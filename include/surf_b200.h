@@ -202,6 +202,11 @@ int surf_render_rays(const surf_scene* s, const surf_net* n, const surf_render_c
 int surf_sdf_points(const surf_scene* s, const surf_net* n, const float* d_pts, int64_t n_pts, float* d_sdf,
                     float* d_grad, int32_t mlp_mode, void* stream);
 
+/* SDFNetworkSparse.forward (sdf_network.py:95-121): the full (n, d_out) output [sdf / scale, lin6 rows 1..d_out-1].
+ * The extra outputs are dead on the render path (implicit_surface.py:95-97); plain fp32 kernel, API completeness. */
+int surf_sdf_full(const surf_scene* s, const surf_net* n, const float* d_pts, int64_t n_pts, float* d_out,
+                  int32_t d_out_dim, void* stream);
+
 /* extract_geometry's SDF query (implicit_surface.py:337-351): u[x,y,z] = -sdf(xs[x],ys[y],zs[z]) on the
  * tensor-product grid of the three coordinate tables (host torch.linspace, uploaded).  Dense (Q16).
  * d_u is (nx,ny,nz) row-major.  sparsify != 0: opt-in fast mode, points whose 4-level voxel mask is 0
@@ -227,6 +232,24 @@ int surf_point_flags(const surf_scene* s, const surf_render_cfg* cfg, const floa
                      uint8_t* d_flags, void* d_workspace, size_t workspace_bytes, void* stream);
 
 /* ---- misc ------------------------------------------------------------------------------- */
+/* ---- marching cubes -----------------------------------------------------------------------
+ * Replaces the host call `mcubes.marching_cubes(u, threshold)` of extract_geometry (implicit_surface.py:353; PyMCubes
+ * 0.1.4 is an un-vendored dependency of the reference).  u is the (nx,ny,nz) row-major fp32 grid surf_sdf_grid wrote;
+ * a corner is inside when u > threshold (u = -sdf).  Two calls so that the caller owns every buffer:
+ *   surf_mc_count  classifies the grid into d_workspace (surf_mc_workspace_bytes) and writes
+ *                  d_counts[0] = number of vertices, d_counts[1] = number of triangles (device int64[2]);
+ *   surf_mc_emit   (same u / dims / threshold / workspace) writes the vertices — (n_vertices,3) fp64 in grid-index
+ *                  coordinates like PyMCubes, x shifted by x_offset for an x-slab — and the (n_triangles,3) int32 vertex
+ *                  ids, oriented with the normal pointing outside (towards smaller u).
+ * Every mesh vertex lies on a grid edge at the linear zero of u - threshold; vertices are shared between the
+ * triangles of neighbouring cells (indexed mesh, watertight inside the grid). */
+size_t surf_mc_workspace_bytes(int32_t nx, int32_t ny, int32_t nz);
+int surf_mc_count(const float* d_u, int32_t nx, int32_t ny, int32_t nz, float threshold, void* d_workspace,
+                  size_t workspace_bytes, int64_t* d_counts, void* stream);
+int surf_mc_emit(const float* d_u, int32_t nx, int32_t ny, int32_t nz, float threshold, const void* d_workspace,
+                 int32_t x_offset, double* d_vertices, int64_t n_vertices, int32_t* d_triangles, int64_t n_triangles,
+                 void* stream);
+
 int surf_version(void);
 const char* surf_last_error(void);
 /* number of kernel launches issued by this library in this process (bench.py's gpu_launches) */

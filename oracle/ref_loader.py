@@ -25,7 +25,8 @@ import torch
 
 
 def find_reference():
-    for cand in (os.environ.get("SURF_REF"), "/root/reference"):
+    for cand in (os.environ.get("SURF_REF"), os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref"),
+                 "/root/reference"):
         if cand and os.path.isdir(os.path.join(cand, "models", "modules")):
             return cand
     return None

@@ -31,9 +31,10 @@ EXPORTS = [
     "surf_scene_set_views",
     "surf_net_create", "surf_net_destroy",
     "surf_render_workspace_bytes", "surf_sample_rays", "surf_render_core", "surf_render_rays",
-    "surf_sdf_points", "surf_sdf_grid",
+    "surf_sdf_points", "surf_sdf_grid", "surf_sdf_full",
     "surf_point_mask", "surf_lookup_sparse", "surf_lookup_feature", "surf_blend", "surf_point_flags",
     "surf_tc_selftest",
+    "surf_mc_workspace_bytes", "surf_mc_count", "surf_mc_emit",
 ]
 
 
@@ -169,6 +170,8 @@ def _declare(lib):
                                      C.c_size_t, vp]
     lib.surf_sdf_points.restype = C.c_int
     lib.surf_sdf_points.argtypes = [vp, vp, vp, i64, vp, vp, i32, vp]
+    lib.surf_sdf_full.restype = C.c_int
+    lib.surf_sdf_full.argtypes = [vp, vp, vp, i64, vp, i32, vp]
     lib.surf_sdf_grid.restype = C.c_int
     lib.surf_sdf_grid.argtypes = [vp, vp, vp, i32, vp, i32, vp, i32, vp, i32, f32, i32, vp]
     lib.surf_point_mask.restype = C.c_int
@@ -181,6 +184,12 @@ def _declare(lib):
     lib.surf_blend.argtypes = [vp, vp, vp, vp, i64, i32, vp, i32, vp]
     lib.surf_tc_selftest.restype = C.c_int
     lib.surf_tc_selftest.argtypes = [vp, vp, vp, i32, i32, i32, vp]
+    lib.surf_mc_workspace_bytes.restype = C.c_size_t
+    lib.surf_mc_workspace_bytes.argtypes = [i32, i32, i32]
+    lib.surf_mc_count.restype = C.c_int
+    lib.surf_mc_count.argtypes = [vp, i32, i32, i32, f32, vp, C.c_size_t, vp, vp]
+    lib.surf_mc_emit.restype = C.c_int
+    lib.surf_mc_emit.argtypes = [vp, i32, i32, i32, f32, vp, i32, vp, i64, vp, i64, vp]
     lib.surf_point_flags.restype = C.c_int
     lib.surf_point_flags.argtypes = [vp, P(RenderCfg), vp, vp, vp, i64, i32, vp, vp, vp, C.c_size_t, vp]
 

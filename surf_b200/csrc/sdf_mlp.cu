@@ -401,6 +401,98 @@ k_sdf_mlp(const DevScene sc, const DevNet net, const PointSource src, float* __r
   cp_async_wait<0>();
 }
 
+// ---------------------------------------------------------------------------------------------
+// Full (n, d_out) output of SDFNetworkSparse.forward (sdf_network.py:95-121): [sdf / scale, lin6 rows 1..].
+// The 128 extra outputs are dead on the render path (implicit_surface.py:95-97), so the hot kernels above only
+// evaluate row 0; this plain fp32 kernel exists for API completeness (`sdf_network(x, volumes, indexes)`).
+// 16 points per 128-thread block, thread = one output neuron, activations in shared memory, weights k-major in
+// global memory (coalesced, L1/L2 resident: 480 KB).
+// ---------------------------------------------------------------------------------------------
+#define FH_PTS 16
+#define FH_NS 160          // row stride of the k-major weight matrices
+__global__ void __launch_bounds__(128)
+k_sdf_full(const DevScene sc, const DevNet net, const float* __restrict__ wfull, const int* __restrict__ woff,
+           const float* __restrict__ pts, int64_t n, int d_out, float* __restrict__ out) {
+  __shared__ float s_in[FH_PTS][160];
+  __shared__ float s_out[FH_PTS][160];
+  __shared__ float s_pe[FH_PTS][28];
+  __shared__ float s_ft[FH_PTS][28];
+  const int tid = threadIdx.x;
+  for (int64_t base = (int64_t)blockIdx.x * FH_PTS; base < n; base += (int64_t)gridDim.x * FH_PTS) {
+    __syncthreads();
+    // features (thread = (point, level)) and positional encoding (thread = point)
+    if (tid < FH_PTS * 4) {
+      const int p = tid >> 2, lv = tid & 3;
+      const int64_t i = base + p;
+      float f7[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (i < n && lv < sc.n_levels) sparse_level<0>(sc, lv, pts[i * 3], pts[i * 3 + 1], pts[i * 3 + 2], nullptr, f7);
+#pragma unroll
+      for (int c = 0; c < 7; ++c) s_ft[p][lv * 7 + c] = f7[c];
+    } else if (tid < FH_PTS * 5) {
+      const int p = tid - FH_PTS * 4;
+      const int64_t i = base + p;
+      float x[3] = {0.f, 0.f, 0.f};
+      if (i < n) { x[0] = pts[i * 3] * net.scale; x[1] = pts[i * 3 + 1] * net.scale; x[2] = pts[i * 3 + 2] * net.scale; }
+      for (int d = 0; d < 3; ++d) s_pe[p][d] = x[d];
+      float fr = 1.0f;
+      for (int f = 0; f < net.multires; ++f) {
+        for (int d = 0; d < 3; ++d) {
+          s_pe[p][3 + 6 * f + d] = sinf(x[d] * fr);
+          s_pe[p][3 + 6 * f + 3 + d] = cosf(x[d] * fr);
+        }
+        fr *= 2.0f;
+      }
+    }
+    __syncthreads();
+    for (int i = tid; i < FH_PTS * net.pe_dim; i += 128) s_in[i / net.pe_dim][i % net.pe_dim] = s_pe[i / net.pe_dim][i % net.pe_dim];
+    __syncthreads();
+    int in_dim = net.pe_dim;
+    for (int l = 0; l < 7; ++l) {
+      const int od = (l == 6) ? d_out : net.out_dim[l];
+      const float* Wl = wfull + woff[l];
+      for (int nb = 0; nb < od; nb += 128) {
+        const int o = nb + tid;
+        float acc[FH_PTS];
+#pragma unroll
+        for (int p = 0; p < FH_PTS; ++p) acc[p] = 0.f;
+        if (o < od) {
+          for (int k = 0; k < in_dim; ++k) {
+            const float w = Wl[(size_t)k * FH_NS + o];
+#pragma unroll
+            for (int p = 0; p < FH_PTS; ++p) acc[p] = fmaf(s_in[p][k], w, acc[p]);
+          }
+          const float b = Wl[(size_t)in_dim * FH_NS + o];        // bias row
+#pragma unroll
+          for (int p = 0; p < FH_PTS; ++p) {
+            float v = acc[p] + b;
+            if (l < 6) {
+              float h, dh;
+              softplus100(v, h, dh);
+              s_out[p][o] = h;
+            } else {
+              const int64_t i = base + p;
+              if (i < n) out[i * d_out + o] = (o == 0) ? v * net.inv_scale : v;
+            }
+          }
+        }
+      }
+      if (l == 6) break;
+      __syncthreads();
+      // next input: [h (out_dim) | PE if the next layer is the skip layer | feats]; the 1/sqrt(2) of the skip concat
+      // is folded into the weights
+      int nd = od;
+      for (int i = tid; i < FH_PTS * od; i += 128) s_in[i / od][i % od] = s_out[i / od][i % od];
+      if (l + 1 == net.skip_layer) {
+        for (int i = tid; i < FH_PTS * net.pe_dim; i += 128) s_in[i / net.pe_dim][od + i % net.pe_dim] = s_pe[i / net.pe_dim][i % net.pe_dim];
+        nd += net.pe_dim;
+      }
+      for (int i = tid; i < FH_PTS * 28; i += 128) s_in[i / 28][nd + i % 28] = s_ft[i / 28][i % 28];
+      in_dim = nd + 28;
+      __syncthreads();
+    }
+  }
+}
+
 // grid pre-pass for the opt-in sparsified extraction (Q16): mask -> list, fill elsewhere
 __global__ void k_grid_sparsify(const DevScene sc, const float* __restrict__ xs, const float* __restrict__ ys,
                                 const float* __restrict__ zs, int nx, int ny, int nz, float fill,
@@ -546,6 +638,31 @@ int surf_build_sdf_weights(const surf_net_inputs* in, surf_net* net, cudaStream_
   if (rc) return rc;
   SURF_CUDA(cudaMemcpyAsync(p, w6.data(), w6.size() * sizeof(float), cudaMemcpyHostToDevice, st));
   net->dev.w6 = (const float*)p;
+  {   // k-major fp32 matrices (+ bias row) of all 7 layers for the full-head kernel k_sdf_full
+    std::vector<float> wf;
+    std::vector<int> off(8, 0);
+    for (int l = 0; l < 7; ++l) {
+      const int O = in->out_dim[l], I = in->in_dim[l];
+      if (O > FH_NS) {
+        surf_set_error("lin%d: out dim %d > %d unsupported", l, O, FH_NS);
+        return -1;
+      }
+      off[l] = (int)wf.size();
+      wf.resize(wf.size() + (size_t)(I + 1) * FH_NS, 0.f);
+      for (int k = 0; k < I; ++k)
+        for (int o = 0; o < O; ++o) wf[off[l] + (size_t)k * FH_NS + o] = W[l][(size_t)o * I + k];
+      for (int o = 0; o < O; ++o) wf[off[l] + (size_t)I * FH_NS + o] = in->h_bias[l][o];
+    }
+    rc = dev_alloc(net, &p, wf.size() * sizeof(float));
+    if (rc) return rc;
+    SURF_CUDA(cudaMemcpyAsync(p, wf.data(), wf.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+    net->w_full = (const float*)p;
+    rc = dev_alloc(net, &p, off.size() * sizeof(int));
+    if (rc) return rc;
+    SURF_CUDA(cudaMemcpyAsync(p, off.data(), off.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    net->w_full_off = (const int*)p;
+    SURF_CUDA(cudaStreamSynchronize(st));
+  }
   SURF_CUDA(cudaStreamSynchronize(st));   // host vectors go out of scope
   net->tc_ok = (in->multires == 4 && skip == 3) ? 1 : 0;
   if (net->tc_ok) {
@@ -597,6 +714,19 @@ extern "C" int surf_sdf_points(const surf_scene* s, const surf_net* n, const flo
   src.pts = d_pts;
   src.n = n_pts;
   return launch_sdf_mlp(s, n, src, d_sdf, d_grad, false, mlp_mode, (cudaStream_t)stream);
+}
+
+extern "C" int surf_sdf_full(const surf_scene* s, const surf_net* n, const float* d_pts, int64_t n_pts, float* d_out,
+                             int32_t d_out_dim, void* stream) {
+  if (n_pts <= 0) return 0;
+  SURF_CHECK_ARG(s && n && d_pts && d_out, "null pointer");
+  SURF_CHECK_ARG(d_out_dim == n->dev.out_dim[6], "d_out_dim must equal the out dim of lin6");
+  const int64_t blocks = (n_pts + FH_PTS - 1) / FH_PTS;
+  const int64_t cap = (int64_t)surf_num_sms() * 16;
+  k_sdf_full<<<(int)(blocks < cap ? blocks : cap), 128, 0, (cudaStream_t)stream>>>(s->dev, n->dev, n->w_full, n->w_full_off,
+                                                                                  d_pts, n_pts, d_out_dim, d_out);
+  SURF_LAUNCH_CHECK();
+  return 0;
 }
 
 extern "C" int surf_sdf_grid(const surf_scene* s, const surf_net* n, const float* d_xs, int32_t nx, const float* d_ys,

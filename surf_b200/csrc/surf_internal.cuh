@@ -93,7 +93,8 @@ struct surf_net {
   void* tc_scratch;                 // softplus' code scratch of sdf_tc2.cu (per-CTA private, L2-resident)
   const uint8_t* blend_tc_w;        // blend_tc.cu: fp16 hi/lo tensor-core operands
   const float* blend_tc_f;          // blend_tc.cu: fp32 small-layer weights and biases
-  const float* w6_full;             // (out6, 160) folded lin6 rows + bias (opt-in full (n,129) head)
+  const float* w_full;              // k-major fp32 matrices (+ bias row) of lin0..lin6 for k_sdf_full (opt-in (n,129) head)
+  const int* w_full_off;            // float offset of each layer in w_full
   int tc_ok;                        // network shape supported by the tensor-core kernels
   float* scratch;                   // sigma' scratch of the FFMA backward pass (per-CTA private)
   size_t scratch_bytes;

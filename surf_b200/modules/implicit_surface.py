@@ -19,7 +19,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from .. import _lib
+from .. import _lib, mesh
 from ..scene import GLOBAL_SCENE_CACHE, PreparedScene
 from .blending_network import BlendingNetwork
 from .sdf_network import SDFNetworkSparse
@@ -322,18 +322,15 @@ class ImplicitSurface(nn.Module):
         return u
 
     def extract_geometry(self, volumes, sparse_idxes, bound_min, bound_max, resolution, threshold):
-        """implicit_surface.py:337-357.  The SDF grid is evaluated on the GPU in one pass; marching cubes
-        stays the host PyMCubes call of the reference (un-vendored third party)."""
+        """implicit_surface.py:337-357.  The SDF grid is evaluated on the GPU in one pass and meshed on the GPU
+        (surf_b200/csrc/marching.cu) — the grid never visits the host; the reference's PyMCubes host call is an
+        un-vendored third party.  Returns numpy (vertices float64 in world units, triangles int64)."""
         scene = volumes if isinstance(volumes, PreparedScene) else self.scene_cache.get(volumes, sparse_idxes)
-        u = self.sdf_grid(scene, bound_min, bound_max, resolution).cpu().numpy()
-        try:
-            import mcubes
-        except ImportError as e:
-            raise RuntimeError("extract_geometry needs PyMCubes for marching cubes (reference dependency, "
-                               "implicit_surface.py:353); use sdf_grid() for the SDF volume itself") from e
-        vertices, triangles = mcubes.marching_cubes(u, threshold)
-        b_max_np = np.asarray([float(v) for v in bound_max], dtype=np.float32)
-        b_min_np = np.asarray([float(v) for v in bound_min], dtype=np.float32)
+        u = self.sdf_grid(scene, bound_min, bound_max, resolution)
+        v, t = mesh.marching_cubes_device(u, float(threshold))
+        vertices, triangles = v.cpu().numpy(), t.cpu().numpy().astype(np.int64)
+        b_max_np = np.asarray([float(v_) for v_ in bound_max], dtype=np.float32)
+        b_min_np = np.asarray([float(v_) for v_ in bound_min], dtype=np.float32)
         vertices = vertices / (resolution - 1.0) * (b_max_np - b_min_np)[None, :] + b_min_np[None, :]
         return vertices, triangles
 
@@ -423,8 +420,11 @@ class ImplicitSurface(nn.Module):
             far = far.repeat(rays_o.shape[0], 1)
         scene = self.prepare(matching_volume, volumes, sparse_idxes, mask_volumes, imgs, features, intrs, c2ws)
         if mode == "val":
+            # the reference hard-wires extract_geometry=True, mesh_resolution=512, threshold=0 here (:416-418);
+            # ``val_options`` (set by surf_b200.runner.validate) may override them, e.g. a smaller mesh for previews
             outputs = self.validate(rays_o, rays_d, near, far, scene, None, None, None, imgs, features, match_features,
-                                    intrs, c2ws, ipts["bound_min"], ipts["bound_max"], ipts["hw"], cos_anneal_ratio, step)
+                                    intrs, c2ws, ipts["bound_min"], ipts["bound_max"], ipts["hw"], cos_anneal_ratio, step,
+                                    **getattr(self, "val_options", {}))
         else:
             outputs = self.render(rays_o, rays_d, near, far, scene, None, None, None, imgs, features, match_features,
                                   intrs, c2ws, cos_anneal_ratio, step)

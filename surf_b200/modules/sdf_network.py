@@ -134,7 +134,15 @@ class SDFNetworkSparse(nn.Module):
         return grad, torch.zeros_like(grad)
 
     def forward(self, inputs, volumes, indexes=None):
-        """The reference returns (n, d_out) = [sdf, 128 hidden features]; the hidden features are dead
-        on the render path (implicit_surface.py:95-97 scatters them and never reads them), so the kernel
-        evaluates only row 0 of lin6.  Returns (n,1)."""
-        return self.sdf(inputs, volumes, indexes)
+        """(n,3) -> (n, d_out) = [sdf / scale, lin6 outputs 1..] exactly like the reference (sdf_network.py:95-121).
+        The extra outputs are dead on the render path (implicit_surface.py:95-97 scatters them and never reads them),
+        so ``sdf`` / ``gradient`` and the fused render kernels evaluate only row 0 of lin6; this entry point runs a plain
+        fp32 kernel (surf_sdf_full)."""
+        scene, net, _ = self._handles(volumes, indexes)
+        x = inputs.detach().to(torch.float32).contiguous()
+        d_out = int(self.dims[-1])
+        out = torch.empty((x.shape[0], d_out), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().surf_sdf_full(scene.handle, net, x.data_ptr(), x.shape[0], out.data_ptr(), d_out,
+                                                 _stream()), "sdf_full")
+        return out

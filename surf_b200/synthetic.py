@@ -155,8 +155,10 @@ def make_scene(nv=3, H=576, W=800, base=88, seed=1, device="cpu", n_levels=4, fe
         parent = m
         flat = m.reshape(-1)
         nvox = int(flat.sum())
-        idx = torch.cumsum(flat, 0, dtype=torch.int64) - 1
-        idx = torch.where(flat, idx, torch.full_like(idx, -1)).reshape(n, n, n)
+        idx = torch.cumsum(flat, 0, dtype=torch.int64)      # in place from here on: 1408^3 int64 is 22 GB
+        idx -= 1
+        idx.masked_fill_(~flat, -1)
+        idx = idx.reshape(n, n, n)
         g.manual_seed(seed + 100 + l)
         vol = torch.randn((nvox, feat_ch), generator=g, device=device, dtype=torch.float32) * 0.1
         masks.append(m.to(torch.float32).reshape(1, 1, n, n, n))

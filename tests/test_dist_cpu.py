@@ -41,6 +41,10 @@ def _worker(rank, world, port, n_rays, res, out_q):
         local = {k: v[r0:r1] for k, v in full.items()}
         got = sdist.gather_image(local, n_rays)
         ok = all(torch.equal(got[k].reshape(full[k].shape), full[k]) for k in full)
+        ig = sdist.ImageGather(n_rays, "cpu")
+        for _ in range(2):              # persistent buffers: a second image through the same object
+            got2 = ig(local)
+            ok = ok and all(torch.equal(got2[k].reshape(full[k].shape), full[k]) for k in full)
         u = torch.rand(res, res, res, generator=g)
         x0, x1 = sdist.shard_planes(res, rank, world)
         ok = ok and torch.equal(sdist.gather_grid(u[x0:x1], res), u)
@@ -53,11 +57,13 @@ def test_gather_image_and_grid_gloo_world2():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, 1000, 9, q)) for r in range(2)]
-    for p in procs:
-        p.start()
-    for p in procs:
-        p.join(120)
-        assert p.exitcode == 0
-    results = dict(q.get(timeout=10) for _ in range(2))
-    assert results == {0: True, 1: True}
+    for n_rays, res in ((1000, 9), (1024, 8), (200, 3)):      # ragged, even, and an EMPTY last shard
+        procs = [ctx.Process(target=_worker, args=(r, 2, port, n_rays, res, q)) for r in range(2)]
+        for p in procs:
+            p.start()
+        for p in procs:
+            p.join(120)
+            assert p.exitcode == 0
+        results = dict(q.get(timeout=10) for _ in range(2))
+        assert results == {0: True, 1: True}, (n_rays, res, results)
+        port = _free_port()

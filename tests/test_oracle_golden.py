@@ -94,3 +94,25 @@ def test_sdf_grid_matches_reference():
     assert_close(gr, g["out"]["wild_grad"], TOL, "out-of-range gradient")
     _, gr2 = O.sdf_gradient_analytic(net, wild, sc.volumes, sc.sparse_idxes)
     assert_close(gr2, g["out"]["wild_grad"], 2e-5, "out-of-range gradient (analytic)")
+
+
+def test_reference_gradient_moves_with_the_last_bit_of_the_position():
+    """The conditioning fact behind helpers.explain_gradient_mismatches: a ONE-ulp shift of the sample position changes
+    the reference's own d sdf / d x by an amount that grows with the volume resolution (trilinear features: derivative
+    changes at (feature difference) / voxel^2).  Measured here on the oracle at two resolutions."""
+    import bench              # repo root is on sys.path (tests/conftest.py)
+    from surf_b200 import synthetic
+    m = bench.build_net(None, seed=0)
+    net = O.OracleNet({k: v.detach() for k, v in m.state_dict().items()})
+    dev = {}
+    for base in (4, 32):
+        sc = synthetic.make_scene(3, 48, 64, base, seed=3, device="cpu")
+        g = torch.Generator().manual_seed(1)
+        pts = torch.nn.functional.normalize(torch.randn(4000, 3, generator=g), dim=1) * (0.5 + 0.02 * torch.randn(4000, 1, generator=g))
+        _, g0 = O.sdf_gradient(net, pts, sc.volumes, sc.sparse_idxes)
+        _, g1 = O.sdf_gradient(net, torch.nextafter(pts, torch.full_like(pts, 10.0)), sc.volumes, sc.sparse_idxes)
+        on_face = O.voxel_face_distance(pts, sc.sparse_idxes) < 2.5
+        d = ((g1 - g0).abs().max(dim=1)[0] / g0.abs().max())[~on_face]
+        dev[base] = float(torch.quantile(d, 0.999))
+    assert dev[32] > 3 * dev[4], dev                  # 8x the resolution: the sensitivity grows with it
+    assert dev[32] > 3e-6, dev                        # already >= 3 % of the 1e-4 budget per ulp at 256^3 (704^3: x2.75)
