@@ -415,7 +415,7 @@ def _seq(x, cw, name, idxs, final_act=True):
 
 
 def blend(net: OracleNet, feat_views, ray_diff, mask, e_ulp=None):
-    """``e_ulp`` (n,V) in {-1,0,+1}: test-only knob that moves the pooling exponentials by that many fp32
+    """``e_ulp`` (n,V) integer: test-only knob that moves the pooling exponentials by that many fp32
     ulps, used by tests/helpers.blend_envelope to measure how ill-conditioned the reference's
     anti-alias weights are at a point (they subtract nearly equal exponentials)."""
     cw = net.color
@@ -428,8 +428,8 @@ def blend(net: OracleNet, feat_views, ray_diff, mask, e_ulp=None):
     if e_ulp is not None:
         up = torch.nextafter(e, torch.full_like(e, 4.0))
         dn = torch.nextafter(e, torch.full_like(e, -4.0))
-        sh = e_ulp[:, :, None]
-        e = torch.where(sh > 0, up, torch.where(sh < 0, dn, e))
+        sh = e_ulp[:, :, None].to(e.dtype)          # any integer number of ulps
+        e = torch.where(sh > 0, e + sh * (up - e), torch.where(sh < 0, e + sh * (e - dn), e))
     wgt = (e - torch.min(e, dim=1, keepdim=True)[0]) * m
     wgt = wgt / (torch.sum(wgt, dim=1, keepdim=True) + 1e-8)
     mean = torch.sum(x * wgt, dim=1, keepdim=True)

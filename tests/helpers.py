@@ -74,28 +74,30 @@ def assert_equal_int(a, b, what=""):
     assert not bool(ne.any()), "%s: %d/%d integer mismatches" % (what, int(ne.sum()), b.numel())
 
 
-def blend_envelope(O, net, fv, rd, mk, n_random=4, seed=0):
+def blend_envelope(O, net, fv, rd, mk, n_random=4, seed=0, ulps=(1, 3)):
     """Conditioning envelope of the reference's anti-alias pooling weights.
 
     weight = (exp(s (dot_v - 1)) - min_v exp(...)) / (sum + 1e-8) subtracts nearly equal fp32 exponentials
     (blending_network.py:76-80).  With 3+ source views of similar viewing angle a ONE-ulp change of one
-    exponential moves the output by up to 0.2 in RGB (measured on the 5-view golden case), and torch's own
-    CPU exp is not correctly rounded (differs from the correctly rounded value in ~2 % of arguments), so
+    exponential moves the output by up to 0.2 in RGB (measured on the 5-view golden case), torch's own
+    CPU exp is not correctly rounded (differs from the correctly rounded value in ~2 % of arguments), the argument
+    s (dot - 1) itself cancels (dot ~ 0.999), and the kernel's exp is ex2.approx(x log2 e) (<= 3 ulp), so
     no independent implementation can match the reference bit-for-bit there.  Returns (reference output,
     per-point envelope) where the envelope is the largest change of the oracle's output when the
-    exponentials move by +-1 ulp (each view alone, both signs, plus random patterns)."""
+    exponentials move by +-k ulp, k in ``ulps`` (each view alone, both signs, plus random patterns)."""
     g = torch.Generator().manual_seed(seed)
     base = O.blend(net, fv, rd, mk)
     n, V = fv.shape[0], fv.shape[1]
     env = torch.zeros(n)
     pats = []
-    for v in range(V):
-        for sgn in (-1, 1):
-            p = torch.zeros(n, V, dtype=torch.int64)
-            p[:, v] = sgn
-            pats.append(p)
-    for _ in range(n_random):
-        pats.append(torch.randint(0, 3, (n, V), generator=g) - 1)
+    for k in ulps:
+        for v in range(V):
+            for sgn in (-k, k):
+                p = torch.zeros(n, V, dtype=torch.int64)
+                p[:, v] = sgn
+                pats.append(p)
+        for _ in range(n_random):
+            pats.append((torch.randint(0, 3, (n, V), generator=g) - 1) * k)
     for p in pats:
         env = torch.maximum(env, (O.blend(net, fv, rd, mk, e_ulp=p) - base).abs().max(dim=1)[0])
     return base, env
@@ -173,16 +175,20 @@ def explain_gradient_mismatches(O, out, ref, rays_o, rays_d, sc, net, what="", r
     env = O.gradient_position_envelope(net, ref, out["mid_z_vals"], rays_o, rays_d, sc.volumes, sc.sparse_idxes)
     err = (gg - gr).abs().max(dim=1)[0]
     tol = rtol * scale + 2.0 * env
-    bad = (err > tol) & cm
-    n = int(bad.sum())
-    if n:
-        dz = (out["mid_z_vals"].cpu().double() - ref["mid_z_vals"].double()).abs().reshape(-1)[bad]
-        dn = rays_d.double().norm(dim=1)[:, None].expand(B, S).reshape(-1)[bad]
-        margin = O.voxel_face_margin(ref["_pts"][bad], sc.sparse_idxes, 2.0 * dz * dn)
-        off = margin >= 2.5
-        assert not bool(off.any()), "%sgradient: %d of %d deviating samples are NOT on a voxel face (worst margin %.1f " \
-            "ulp, worst err %.3e vs tolerance %.3e, scale %.3e)" % (what, int(off.sum()), n, float(margin.max()),
-                                                                   float(err[bad][off].max()), float(tol[bad][off].min()), scale)
+    dev = (err > rtol * scale) & cm                       # candidates: look at each one
+    bad = torch.zeros_like(dev)
+    if bool(dev.any()):
+        dz = (out["mid_z_vals"].cpu().double() - ref["mid_z_vals"].double()).abs().reshape(-1)[dev]
+        dn = rays_d.double().norm(dim=1)[:, None].expand(B, S).reshape(-1)[dev]
+        margin = O.voxel_face_margin(ref["_pts"][dev], sc.sparse_idxes, 2.0 * dz * dn)
+        on_face = margin < 2.5
+        off = ~on_face & (err[dev] > tol[dev])
+        assert not bool(off.any()), "%sgradient: %d of %d deviating samples are beyond 1e-4 + position envelope and NOT on " \
+            "a voxel face (worst margin %.1f ulp, worst err %.3e vs tolerance %.3e, scale %.3e)" % (
+                what, int(off.sum()), int(dev.sum()), float(margin[off].max()), float(err[dev][off].max()),
+                float(tol[dev][off].min()), scale)
+        bad[dev.nonzero()[:, 0][on_face]] = True         # a sample ON a face: its ray is counted, not compared
+        n = int(bad.sum())
         assert n <= max(3, int(max_frac * int(cm.sum()))), "%sgradient: %d on-face samples of %d" % (what, n, int(cm.sum()))
     ok = cm & ~bad
     worst = float((err[ok] / tol[ok]).max()) if bool(ok.any()) else 0.0
@@ -213,8 +219,18 @@ def check_composited(O, out, ref, sc, net, rays_o, rays_d, rows=None, per_sample
     env_pt[cm] = env_p
     cerr = (col_g - ref["_color"].reshape(-1, 3)).abs().max(dim=1)[0]
     bad = (cerr > RTOL_FP32 + 2.0 * env_pt) & keep_p
-    assert not bool(bad.any()), what + "per-point colour: %d points beyond 1e-4 + conditioning envelope (max %.3e)" % (
-        int(bad.sum()), float(cerr[keep_p].max()))
+    if bool(bad.any()):          # diagnostics of the offending points (what makes them special?)
+        sel = bad[cm]
+        e = torch.exp(torch.abs(net.color["s"]) * (rd[sel][..., 3] - 1)).double()
+        ulp = torch.finfo(torch.float32).eps * e
+        spread = (e.max(dim=1)[0] - e.min(dim=1)[0]) / ulp.max(dim=1)[0]
+        border = O.projection_border_distance(pv[sel], sc.imgs, sc.intrs, sc.c2ws, sc.features)
+        msg = "; ".join("err %.2e env %.2e mask %s exp-spread %.1f ulp border %.2e px col_gpu %s col_ref %s" % (
+            float(cerr[cm][sel][i]), float(env_p[sel][i]), mv[sel][i].tolist(), float(spread[i]), float(border[i]),
+            [round(float(v), 5) for v in col_g[cm][sel][i]], [round(float(v), 5) for v in ref["_color"].reshape(-1, 3)[cm][sel][i]])
+            for i in range(min(4, int(sel.sum()))))
+        raise AssertionError(what + "per-point colour: %d points beyond 1e-4 + conditioning envelope (max %.3e): %s" % (
+            int(bad.sum()), float(cerr[keep_p].max()), msg))
     inv_s = torch.exp(net.variance * 10.0).clip(1e-6, 1e6)
     rot = torch.inverse(sc.c2ws[0, :3, :3])
     env, _ = composite_envelope(O, ref, sdf_g, grad_g, col_g, rays_o, rays_d, inv_s, rot, per_sample=per_sample)
