@@ -326,7 +326,7 @@ def run_reference(args):
             print("reference tree not usable (%s): timing the oracle port" % e, file=sys.stderr)
             ref_net = None
     if args.reference_kind == "reference" and ref_net is None:
-        print(json.dumps({"impl": "reference", "unavailable": "reference source tree not reachable on this box"}))
+        emit({"impl": "reference", "unavailable": "reference source tree not reachable on this box"})
         return
 
     def step_port(oo, dd, tt):
@@ -377,7 +377,7 @@ def run_reference(args):
     }
     if port is not None:
         line["cpu_baseline_port"] = port
-    print(json.dumps(line))
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -650,12 +650,27 @@ def run_gpu(args):
         if cpu is not None:
             line["cpu_baseline"] = cpu
             line["parity"] = parity
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_JSON_OUT = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the process' original stdout; everything else (NCCL's version banner, library chatter)
+    was redirected to stderr in main()."""
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)                      # C-level writes to fd 1 (e.g. "NCCL version ...") must not pollute the JSON line
     args = parse()
     if args.impl == "reference":
         run_reference(args)

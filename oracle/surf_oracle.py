@@ -597,6 +597,37 @@ def gradient_position_envelope(net, ref, mid_gpu, rays_o, rays_d, volumes, index
     return out
 
 
+def color_position_envelope(net, ref, mid_gpu, rays_o, rays_d, imgs, intrs, c2ws, features):
+    """Conditioning of the blended colour with respect to the sample position / its projection.
+
+    A sample projects to pixel coordinates of magnitude ~10^2..10^3, whose fp32 spacing is 3e-5..6e-5 px; the two paths
+    form the projection in a different operation order (torch: inverse(c2w) @ p, K @ cam; the kernel: precomputed w2c
+    rows) and their sample depths differ by an ulp or two, so the bilinear taps are taken ~1e-4 px apart — and the
+    sampled images / feature maps change by O(1) per pixel (white noise in the synthetic scenes).  The per-point colour
+    is therefore held to 1e-4 + 2 x (pooling-weight envelope + this envelope): the change of the ORACLE's colour when
+    the point moves by +-(|mid_gpu - mid_ref| * |d| + 2.5e-7) along the ray and by the same length along (1,1,1)/sqrt 3
+    (2.5e-7 in world units = 1.8e-4 px at the benchmarked geometry = 3 ulp of a pixel coordinate).
+    Returns the (P,) envelope (max over RGB) for the evaluated samples (0 elsewhere)."""
+    B, S = ref["mid_z_vals"].shape
+    cm = ref["_compute_mask"]
+    dz = (torch.as_tensor(mid_gpu).detach().cpu().double() - ref["mid_z_vals"].double()).abs().reshape(-1)[cm]
+    dirs = rays_d[:, None, :].expand(B, S, 3).reshape(-1, 3)[cm].double()
+    pts = ref["_pts"][cm]
+    step = (dz * dirs.norm(dim=1) + 2.5e-7)[:, None]
+    unit = dirs / dirs.norm(dim=1, keepdim=True)
+    diag = torch.full_like(unit, 3.0 ** -0.5)
+    fv, rd, mk = lookup_feature(pts, imgs, intrs, c2ws, features)
+    c0 = blend(net, fv, rd, mk).double()
+    env = torch.zeros(pts.shape[0], dtype=torch.float64)
+    for shift in (unit * step, -unit * step, diag * step):
+        fv1, rd1, mk1 = lookup_feature((pts.double() + shift).float(), imgs, intrs, c2ws, features)
+        c1 = blend(net, fv1, rd1, mk1).double()
+        env = torch.maximum(env, (c1 - c0).abs().max(dim=1)[0])
+    out = torch.zeros(B * S, dtype=torch.float64)
+    out[cm] = env
+    return out
+
+
 RAY_KEYS = ("color_fine", "render_depth", "sdf_depth", "normal", "val_normal", "weight_sum")
 
 

@@ -217,6 +217,10 @@ def check_composited(O, out, ref, sc, net, rays_o, rays_d, rows=None, per_sample
     _, env_p = blend_envelope(O, net, fv, rd, mv, n_random=2)
     env_pt = torch.zeros(B * S)
     env_pt[cm] = env_p
+    # ... and of the projection (oracle.color_position_envelope)
+    env_pos = O.color_position_envelope(net, ref, out["mid_z_vals"], rays_o, rays_d, sc.imgs, sc.intrs, sc.c2ws,
+                                        sc.features).float()
+    env_pt = env_pt + env_pos
     cerr = (col_g - ref["_color"].reshape(-1, 3)).abs().max(dim=1)[0]
     bad = (cerr > RTOL_FP32 + 2.0 * env_pt) & keep_p
     if bool(bad.any()):          # diagnostics of the offending points (what makes them special?)
@@ -224,7 +228,7 @@ def check_composited(O, out, ref, sc, net, rays_o, rays_d, rows=None, per_sample
         e = torch.exp(torch.abs(net.color["s"]) * (rd[sel][..., 3] - 1)).double()
         ulp = torch.finfo(torch.float32).eps * e
         spread = (e.max(dim=1)[0] - e.min(dim=1)[0]) / ulp.max(dim=1)[0]
-        border = O.projection_border_distance(pv[sel], sc.imgs, sc.intrs, sc.c2ws, sc.features)
+        border = O.projection_border_distance(pv[sel], sc.intrs, sc.c2ws, sc.features)
         msg = "; ".join("err %.2e env %.2e mask %s exp-spread %.1f ulp border %.2e px col_gpu %s col_ref %s" % (
             float(cerr[cm][sel][i]), float(env_p[sel][i]), mv[sel][i].tolist(), float(spread[i]), float(border[i]),
             [round(float(v), 5) for v in col_g[cm][sel][i]], [round(float(v), 5) for v in ref["_color"].reshape(-1, 3)[cm][sel][i]])
