@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define SURF_ABI_VERSION 2
+#define SURF_ABI_VERSION 3
 #define SURF_MAX_LEVELS 4
 #define SURF_MAX_VIEWS 8       /* source views (nv-1) */
 #define SURF_MAX_STAGES 4
@@ -175,6 +175,10 @@ typedef struct surf_render_outputs {
   uint8_t* d_point_views;     /* (P,) bitmask of valid source views */
   int32_t* d_prev_idx;        /* (B,) first zero-crossing index */
   float* d_alpha;             /* (B,S) */
+  /* inputs of the training extras (nullable): the raw zero-crossing depth of every ray, before the validity mask
+   * (implicit_surface.py:210), and the largest sample depth of the call (:219; zero it first, accumulated by max) */
+  float* d_z_cross;           /* (B,) */
+  float* d_z_max;             /* (1,) */
 } surf_render_outputs;
 
 size_t surf_render_workspace_bytes(int64_t n_rays, int32_t n_samples_total, int32_t n_src_views);
@@ -232,6 +236,29 @@ int surf_point_flags(const surf_scene* s, const surf_render_cfg* cfg, const floa
                      uint8_t* d_flags, void* d_workspace, size_t workspace_bytes, void* stream);
 
 /* ---- misc ------------------------------------------------------------------------------- */
+/* ---- training extras ------------------------------------------------------------------------
+ * The training-only tail of render_core (implicit_surface.py:218-245) + surface_patch_warp2 / patch_homography
+ * (projector.py:560-645): surface point pts_sdf0 = o + d * clamp(z_cross) (Q15), its unit normal in the reference
+ * camera frame (third SDF-MLP pass), and the plane-homography warp of a patch_size^2 pixel patch of the 12-channel
+ * feature maps [features[0] | up(features[1]) | up(features[2])] of the scene's current views.
+ * The 3x3 camera matrices are formed on the HOST with the reference's own torch ops (inverse, matmul):
+ *   R0t = c2w0[:3,:3]^T, t0 = -R0t c2w0[:3,3], K0 = intr0[:3,:3], K0inv = inverse(intr)[0,:3,:3],
+ *   Ksrc[v] = intr[v+1][:3,:3], Rrel[v] = c2w[v+1][:3,:3]^T c2w0[:3,:3], RC[v] = c2w[v+1][:3,:3]^T (C0 - C[v+1]).
+ * Outputs: d_ref_val (1,B,P,12), d_src_val (V,B,P,12) fp32 (P = patch_size^2), d_pts_sdf0 (B,3), d_normal_sdf0 (B,3,
+ * nullable).  Takes the scene non-const: the 12-channel maps live behind the handle and are rebuilt after
+ * surf_scene_set_views. */
+typedef struct surf_extras_params {
+  float R0t[9], t0[3], K0[9], K0inv[9];
+  float Ksrc[SURF_MAX_VIEWS][9], Rrel[SURF_MAX_VIEWS][9], RC[SURF_MAX_VIEWS][3];
+  int32_t n_src;
+  int32_t patch_size;           /* 11 */
+} surf_extras_params;
+size_t surf_extras_workspace_bytes(int64_t n_rays);
+int surf_render_extras(surf_scene* s, const surf_net* n, const surf_extras_params* p, const float* d_rays_o,
+                       const float* d_rays_d, const float* d_z_cross, const float* d_z_max, int64_t n_rays,
+                       float* d_pts_sdf0, float* d_normal_sdf0, float* d_ref_val, float* d_src_val, void* d_workspace,
+                       size_t workspace_bytes, int32_t mlp_mode, void* stream);
+
 /* ---- marching cubes -----------------------------------------------------------------------
  * Replaces the host call `mcubes.marching_cubes(u, threshold)` of extract_geometry (implicit_surface.py:353; PyMCubes
  * 0.1.4 is an un-vendored dependency of the reference).  u is the (nx,ny,nz) row-major fp32 grid surf_sdf_grid wrote;

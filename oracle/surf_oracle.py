@@ -558,7 +558,7 @@ def composite(rays_o, rays_d, mid_z, dists, vmask, sdf, grad, color, inv_s, rot0
             "weight_max": torch.max(weights, dim=-1, keepdim=True)[0], "color_fine": color_fine, "normal": normal,
             "val_normal": val_normal, "render_depth": render_depth, "gradient_error": gradient_error,
             "inside_sphere": inside, "mid_inside_sphere": mid_inside, "sdf_depth": sdf_depth, "prev_idx": i0,
-            "crossing_cos": cosab, "crossing_score": score.sum(dim=1, keepdim=True)}
+            "crossing_cos": cosab, "crossing_score": score.sum(dim=1, keepdim=True), "z_cross": z_cross}
 
 
 # ----------------------------------------------------------------------------------------------
@@ -684,11 +684,111 @@ def composite_envelope(ref, sdf_g, grad_g, color_g, rays_o, rays_d, inv_s, rot0_
 
 
 # ----------------------------------------------------------------------------------------------
+# training extras  (implicit_surface.py:172, 218-245; projector.py:560-645)
+# ----------------------------------------------------------------------------------------------
+def sdf_gradient_smooth(net: OracleNet, pts: torch.Tensor, volumes, indexes):
+    """sdf_network.gradient (sdf_network.py:129-152): first-order gradient and `smooth` = d/dx of sum_j (d sdf / d x_j)
+    = Hessian . (1,1,1), by double autograd like the reference.  Returns (grad (n,3), smooth (n,3)), detached."""
+    with torch.enable_grad():
+        x = pts.detach().clone().requires_grad_(True)
+        y = sdf_only(net, x, volumes, indexes)
+        (g,) = torch.autograd.grad(y, x, torch.ones_like(y), create_graph=True)
+        (sm,) = torch.autograd.grad(g, x, torch.ones_like(g))
+    return g.detach(), sm.detach()
+
+
+def warp_feature_maps(features):
+    """implicit_surface.py:229-241: the 12-channel maps the patch loss compares = level-0 features, level-1 and
+    level-2 features bilinearly up-sampled to the level-0 size (F.interpolate, align_corners=False).  (nv,12,H,W)."""
+    f0 = features[0]
+    f1 = F.interpolate(features[1], size=f0.shape[-2:], mode="bilinear")
+    f2 = F.interpolate(features[2], size=f0.shape[-2:], mode="bilinear")
+    return torch.cat([f0, f1, f2], dim=1)
+
+
+def patch_homography(H, uv):
+    """projector.py:631-645.  H (B,V,3,3), uv (B,121,2) -> (V, B*121, 2) warped pixel coordinates."""
+    B, V = H.shape[0], H.shape[1]
+    hom = torch.cat([uv, torch.ones_like(uv[..., :1])], dim=-1)              # (B,121,3)
+    t = torch.einsum("bvik,bok->vboi", H, hom)                                # (V,B,121,3)
+    t = t.reshape(V, -1, 3)
+    return t[..., :2] / (t[..., 2:] + 1e-8)
+
+
+def surface_patch_warp2(pts_sdf0, normals, images, intrs, c2ws, patch_size=11, pixel_shift=None):
+    """projector.py:560-628.  pts_sdf0 (B,1,3) world points, normals (B,1,3) unit normals in the REFERENCE camera
+    frame, images (nv,C,H,W).  Plane-induced homography of an 11x11 pixel patch around the projection of each point
+    into every source view; -> ref values (1,B,121,C), source values (V,B,121,C)."""
+    B = pts_sdf0.shape[0]
+    K_inv = torch.inverse(intrs)
+    R0t = c2ws[0, :3, :3].permute(1, 0).contiguous()
+    xyz = torch.matmul(R0t, pts_sdf0.permute(0, 2, 1).contiguous())           # (B,3,1)
+    xyz = xyz + (-torch.matmul(R0t, c2ws[0, :3, 3, None]))
+    pts_ref = xyz
+    proj = torch.matmul(intrs[0, :3, :3], xyz)
+    disp = torch.matmul(normals, pts_ref)                                       # (B,1,1)
+    K_ref_inv = K_inv[0, :3, :3]
+    K_src = intrs[1:, :3, :3]
+    V = K_src.shape[0]
+    R_src = c2ws[1:, :3, :3].permute(0, 2, 1).contiguous()
+    R_rel = torch.matmul(R_src, c2ws[0, :3, :3])
+    C_rel = c2ws[0, :3, 3][None, ...] - c2ws[1:, :3, 3]
+    tmp = torch.matmul(R_src, C_rel[..., None])                                 # (V,3,1)
+    tmp = torch.matmul(tmp[None, ...].expand(B, V, 3, 1), normals.expand(B, V, 3)[..., None].permute(0, 1, 3, 2))
+    tmp = R_rel[None, ...].expand(B, V, 3, 3) + tmp / (disp[..., None] + 1e-10)
+    tmp = torch.matmul(K_src[None, ...].expand(B, V, 3, 3), tmp)
+    Hom = torch.matmul(tmp, K_ref_inv[None, None, ...])
+    px = proj[:, 0, 0] / (proj[:, 2, 0] + 1e-8)
+    py = proj[:, 1, 0] / (proj[:, 2, 0] + 1e-8)
+    pixels = torch.stack([px, py], dim=-1).float()
+    hp = patch_size // 2
+    total = (2 * hp + 1) ** 2
+    off = torch.arange(-hp, hp + 1)
+    off = torch.stack(torch.meshgrid(off, off, indexing="ij")[::-1], dim=-1).view(1, -1, 2).type_as(pixels)
+    patch = pixels.view(B, 1, 2) + off.float()                                  # (B,121,2)
+    ref_img, src_imgs = images[0], images[1:]
+    h, w = ref_img.shape[-2:]
+    grid = patch_homography(Hom, patch)
+    if pixel_shift is not None:       # checker only: sensitivity of the bilinear taps to the last bits of a pixel coordinate
+        grid = grid + torch.as_tensor(pixel_shift, dtype=grid.dtype)
+        patch = patch + torch.as_tensor(pixel_shift, dtype=patch.dtype)
+    grid = torch.stack([2 * grid[:, :, 0] / (w - 1) - 1.0, 2 * grid[:, :, 1] / (h - 1) - 1.0], dim=-1)
+    sampled = F.grid_sample(src_imgs, grid.view(V, -1, 1, 2), align_corners=True)
+    sampled = sampled.view(V, -1, B, total).permute(0, 2, 3, 1).contiguous()
+    pg = torch.stack([2 * patch[:, :, 0] / (w - 1) - 1.0, 2 * patch[:, :, 1] / (h - 1) - 1.0], dim=-1)
+    refv = F.grid_sample(ref_img[None, ...], pg.view(1, -1, 1, 2), align_corners=True)
+    refv = refv.view(1, -1, B, total).permute(0, 2, 3, 1).contiguous()
+    return refv, sampled, {"disp": disp.reshape(B), "pixels": pixels, "grid": grid.view(V, B, total, 2)}
+
+
+def render_extras(net: OracleNet, rays_o, rays_d, z_vals, z_cross, inside, gradients, volumes, indexes, features,
+                  intrs, c2ws, smooth=True):
+    """The training-only tail of render_core (implicit_surface.py:172, 218-245): `smooth_error`, the surface point
+    `pts_sdf0` (zero-crossing depth clamped to [0, max z_vals of the CHUNK], Q15), its unit normal in the reference
+    camera frame (third MLP pass), and the warped 11x11 feature patches."""
+    B = rays_o.shape[0]
+    z0 = torch.where(z_cross < 0, torch.zeros_like(z_cross), z_cross)
+    z0 = torch.where(z0 > torch.max(z_vals), torch.zeros_like(z0), z0)
+    pts_sdf0 = rays_o[:, None, :] + rays_d[:, None, :] * z0[..., :, None]       # (B,1,3)
+    _, g0 = sdf_gradient(net, pts_sdf0.reshape(-1, 3), volumes, indexes)
+    g0 = g0.reshape(B, 1, 3)
+    n0 = torch.linalg.norm(g0, ord=2, dim=-1, keepdim=True)
+    n0 = torch.where(n0 <= 0, torch.ones_like(n0) * 1e-8, n0)
+    g0 = g0 / n0
+    g0 = torch.matmul(c2ws[0, :3, :3].permute(1, 0).contiguous()[None, ...],
+                      g0.permute(0, 2, 1).contiguous()).permute(0, 2, 1).contiguous()
+    refv, sampled, dbg = surface_patch_warp2(pts_sdf0, g0, warp_feature_maps(features), intrs, c2ws)
+    out = {"ref_gray_val": refv, "sampled_gray_val": sampled, "_pts_sdf0": pts_sdf0.reshape(B, 3),
+           "_normal_sdf0": g0.reshape(B, 3), "_disp": dbg["disp"], "_patch_grid": dbg["grid"]}
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
 # render_core  (implicit_surface.py:64-266; quirks Q2, Q5-Q12)
 # ----------------------------------------------------------------------------------------------
 def render_core(net: OracleNet, rays_o, rays_d, z_vals, volumes, indexes, mask_volumes, features,
                 imgs, intrs, c2ws, cos_anneal_ratio=1.0, pts_random: Optional[torch.Tensor] = None,
-                return_stages=False):
+                return_stages=False, extras=False):
     B, S = z_vals.shape
     sample_dist = 2.0 / net.n_samples[0]
     dists = z_vals[:, 1:] - z_vals[:, :-1]
@@ -751,6 +851,13 @@ def render_core(net: OracleNet, rays_o, rays_d, z_vals, volumes, indexes, mask_v
         "inside_sphere": inside,
         "mid_inside_sphere": mid_inside,
     }
+    if extras:
+        # smooth_error (:172): masked-out samples carry smooth = 0 (:99,:108)
+        smooth = torch.zeros(P, 3)
+        smooth[compute] = sdf_gradient_smooth(net, pv, volumes, indexes)[1]
+        out["smooth_error"] = (torch.linalg.norm(smooth, ord=2, dim=-1).reshape(B, S) * inside).sum() / (inside.sum() + 1e-5)
+        out.update(render_extras(net, rays_o, rays_d, z_vals, comp["z_cross"], inside, g3, volumes, indexes, features,
+                                 intrs, c2ws))
     if return_stages:
         out.update({"_pts": pts, "_voxel_mask": vmask, "_compute_mask": compute, "_sdf": sdf,
                     "_color": color.reshape(B, S, 3), "_view_mask": view_mask, "_alpha": alpha,
@@ -761,7 +868,7 @@ def render_core(net: OracleNet, rays_o, rays_d, z_vals, volumes, indexes, mask_v
 
 def render(net: OracleNet, rays_o, rays_d, near, far, matching_volume, volumes, indexes, mask_volumes,
            imgs, features, intrs, c2ws, cos_anneal_ratio=1.0, t_rand=None, pts_random=None,
-           return_stages=False):
+           return_stages=False, extras=False):
     """ImplicitSurface.render (implicit_surface.py:268-335).  With t_rand/pts_random = None the
     jitter and the random points are drawn from torch's global CPU generator in the reference's
     order (Q1), so ``torch.manual_seed(s); render(...)`` matches the reference stream."""
@@ -772,7 +879,7 @@ def render(net: OracleNet, rays_o, rays_d, near, far, matching_volume, volumes, 
         t_rand = draw_t_rand(rays_o.shape[0], len(net.n_samples))
     z, surf_z = sample_z(net, rays_o, rays_d, near, far, matching_volume, t_rand)
     out = render_core(net, rays_o, rays_d, z, volumes, indexes, mask_volumes, features, imgs, intrs, c2ws,
-                      cos_anneal_ratio, pts_random, return_stages)
+                      cos_anneal_ratio, pts_random, return_stages, extras)
     if return_stages:
         out["_z_vals"] = z
         out["_surf_z"] = surf_z

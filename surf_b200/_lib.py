@@ -14,7 +14,7 @@ MAX_LEVELS = 4
 MAX_VIEWS = 8
 MAX_STAGES = 4
 SDF_LAYERS = 7
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 # MLP kernel family, chosen per call (include/surf_b200.h SURF_MLP_*)
 MLP_FFMA = 0        # fp32 CUDA-core kernels: the parity anchor
@@ -35,6 +35,7 @@ EXPORTS = [
     "surf_point_mask", "surf_lookup_sparse", "surf_lookup_feature", "surf_blend", "surf_point_flags",
     "surf_tc_selftest",
     "surf_mc_workspace_bytes", "surf_mc_count", "surf_mc_emit",
+    "surf_extras_workspace_bytes", "surf_render_extras",
 ]
 
 
@@ -121,7 +122,15 @@ RENDER_OUTPUT_FIELDS = [
     "d_color_fine", "d_render_depth", "d_sdf_depth", "d_normal", "d_val_normal", "d_weights", "d_weight_sum",
     "d_weight_max", "d_valid_mask", "d_inside_sphere", "d_mid_inside_sphere", "d_mid_z_vals", "d_gradients",
     "d_sdf", "d_gradient_error_sums", "d_point_flags", "d_point_color", "d_point_views", "d_prev_idx", "d_alpha",
+    "d_z_cross", "d_z_max",
 ]
+
+
+class ExtrasParams(C.Structure):
+    """surf_extras_params (include/surf_b200.h)."""
+    _fields_ = [("R0t", C.c_float * 9), ("t0", C.c_float * 3), ("K0", C.c_float * 9), ("K0inv", C.c_float * 9),
+                ("Ksrc", (C.c_float * 9) * MAX_VIEWS), ("Rrel", (C.c_float * 9) * MAX_VIEWS),
+                ("RC", (C.c_float * 3) * MAX_VIEWS), ("n_src", C.c_int32), ("patch_size", C.c_int32)]
 
 
 class RenderOutputs(C.Structure):
@@ -184,6 +193,10 @@ def _declare(lib):
     lib.surf_blend.argtypes = [vp, vp, vp, vp, i64, i32, vp, i32, vp]
     lib.surf_tc_selftest.restype = C.c_int
     lib.surf_tc_selftest.argtypes = [vp, vp, vp, i32, i32, i32, vp]
+    lib.surf_extras_workspace_bytes.restype = C.c_size_t
+    lib.surf_extras_workspace_bytes.argtypes = [i64]
+    lib.surf_render_extras.restype = C.c_int
+    lib.surf_render_extras.argtypes = [vp, vp, P(ExtrasParams), vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, C.c_size_t, i32, vp]
     lib.surf_mc_workspace_bytes.restype = C.c_size_t
     lib.surf_mc_workspace_bytes.argtypes = [i32, i32, i32]
     lib.surf_mc_count.restype = C.c_int

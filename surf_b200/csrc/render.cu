@@ -133,7 +133,7 @@ k_composite(const DevScene sc, int64_t B, int S, float sample_dist, float inv_s,
       // ---- first zero crossing (Q12) ----
       const int i0 = first_cross < 0 ? 0 : first_cross;   // argmax of an all-zero row is 0
       const int i1 = i0 + 1;
-      float sdf_depth = 0.f, mid_in = 0.f;
+      float sdf_depth = 0.f, mid_in = 0.f, z_cross = 0.f;
       if (i1 < S) {
         const int64_t a = p0 + i0, b = p0 + i1;
         auto mid_of = [&](int j) {
@@ -156,8 +156,12 @@ k_composite(const DevScene sc, int64_t B, int S, float sample_dist, float inv_s,
         const float s1 = sdf[a], s2 = sdf[b];
         const float z0 = (s1 * zb - s2 * za) / (s1 - s2 + 1e-10f);
         sdf_depth = z0 * camz * mid_in;
+        z_cross = z0;
       }
       if (out.d_sdf_depth) out.d_sdf_depth[r] = sdf_depth;
+      if (out.d_z_cross) out.d_z_cross[r] = z_cross;
+      // max(z_vals) of the call (implicit_surface.py:219): sample depths are sorted and positive -> integer max
+      if (out.d_z_max) atomicMax(reinterpret_cast<int*>(out.d_z_max), __float_as_int(z_vals[p0 + S - 1]));
       if (out.d_mid_inside_sphere) out.d_mid_inside_sphere[r] = mid_in;
       if (out.d_prev_idx) out.d_prev_idx[r] = i0;
     }

@@ -199,6 +199,7 @@ extern "C" void surf_scene_destroy(surf_scene* s) {
   for (int i = 0; i < s->n_owned; ++i) cudaFree(s->owned[i]);
   for (int i = 0; i < 4; ++i)
     if (s->view_buf[i]) cudaFree(s->view_buf[i]);
+  if (s->warp12) cudaFree(s->warp12);
   delete s;
 }
 
@@ -236,6 +237,7 @@ extern "C" int surf_scene_set_views(surf_scene* s, const surf_scene_views* in, v
   DevScene& d = s->dev;
   d.nv = in->n_views;
   d.V = in->n_views - 1;
+  s->views_version++;
   if (in->d_imgs) {
     SURF_CHECK_ARG(in->n_feat_levels == 4, "4 feature pyramid levels expected");
     SURF_CHECK_ARG(in->img_h >= 8 && in->img_w >= 8, "image too small");

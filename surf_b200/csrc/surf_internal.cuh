@@ -37,6 +37,10 @@ struct surf_scene {
   int n_owned;
   void* view_buf[4];                      // NHWC image / feature maps of the current views (surf_scene_set_views)
   size_t view_bytes[4];
+  int views_version;                      // bumped by surf_scene_set_views
+  void* warp12;                           // extras.cu: 12-channel warp maps of the current views, NHWC
+  size_t warp_bytes;
+  int warp_version;                       // views_version the maps were built from
   surf_scene_stats stats;
   int64_t nvox[SURF_MAX_LEVELS];
 };

@@ -26,6 +26,7 @@ from .sdf_network import SDFNetworkSparse
 from .variance_network import SingleVarianceNetwork
 
 N_RANDOM_PTS = 1024     # implicit_surface.py:174
+PATCH_SIZE = 11         # projector.py:560
 
 
 def _stream():
@@ -170,6 +171,8 @@ class ImplicitSurface(nn.Module):
             out("mid_inside_sphere", (B, 1))
             out("mid_z_vals", (B, S))
             out("gradient_error_sums", (2,), zero=True)
+            out("z_cross", (B,))
+            out("z_max", (1,), zero=True)
         if stages:
             out("point_flags", (B * S,), torch.uint8)
             out("point_color", (B * S, 3), zero=True)
@@ -231,6 +234,59 @@ class ImplicitSurface(nn.Module):
         # extrapolating trilinear weights of a far-away point overflow (inf * 0 would be NaN)
         return torch.where(m[:, None].bool(), s, torch.zeros_like(s))
 
+    def _render_extras(self, t, scene, rays_o, rays_d, intrs, c2ws):
+        """The training-only tail of render_core (implicit_surface.py:218-245): surface point, its normal (third MLP
+        pass) and surface_patch_warp2 (projector.py:560-645) in one C call.  The 3x3 camera matrices are formed on the
+        host with the reference's own torch ops."""
+        lib = _lib.load()
+        dev = rays_o.device
+        B = rays_o.shape[0]
+        V = scene.n_src_views
+        intr = intrs.detach().float().cpu()
+        c2w = c2ws.detach().float().cpu()
+        p = _lib.ExtrasParams()
+        R0t = c2w[0, :3, :3].permute(1, 0).contiguous()
+        t0 = -torch.matmul(R0t, c2w[0, :3, 3, None])
+        K_inv = torch.inverse(intr)
+        R_src = c2w[1:, :3, :3].permute(0, 2, 1).contiguous()
+        R_rel = torch.matmul(R_src, c2w[0, :3, :3])
+        RC = torch.matmul(R_src, (c2w[0, :3, 3][None, ...] - c2w[1:, :3, 3])[..., None])
+        p.R0t[:] = R0t.reshape(-1).tolist()
+        p.t0[:] = t0.reshape(-1).tolist()
+        p.K0[:] = intr[0, :3, :3].reshape(-1).tolist()
+        p.K0inv[:] = K_inv[0, :3, :3].reshape(-1).tolist()
+        for v in range(V):
+            p.Ksrc[v][:] = intr[v + 1, :3, :3].reshape(-1).tolist()
+            p.Rrel[v][:] = R_rel[v].reshape(-1).tolist()
+            p.RC[v][:] = RC[v].reshape(-1).tolist()
+        p.n_src = V
+        p.patch_size = PATCH_SIZE
+        npx = PATCH_SIZE * PATCH_SIZE
+        f32 = dict(dtype=torch.float32, device=dev)
+        pts0 = torch.empty((B, 3), **f32)
+        nrm0 = torch.empty((B, 3), **f32)
+        ref_val = torch.empty((1, B, npx, 12), **f32)
+        src_val = torch.empty((V, B, npx, 12), **f32)
+        with torch.cuda.device(dev):
+            ws_bytes = int(lib.surf_extras_workspace_bytes(B))
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            _lib.check(lib.surf_render_extras(scene.handle, self.net_handle(), C.byref(p), rays_o.data_ptr(),
+                                              rays_d.data_ptr(), t["z_cross"].data_ptr(), t["z_max"].data_ptr(), B,
+                                              pts0.data_ptr(), nrm0.data_ptr(), ref_val.data_ptr(), src_val.data_ptr(),
+                                              ws.data_ptr(), ws_bytes, int(self.mlp_mode), _stream()), "render_extras")
+        return {"ref_gray_val": ref_val, "sampled_gray_val": src_val, "_pts_sdf0": pts0, "_normal_sdf0": nrm0}
+
+    def _extras(self, t, scene, rays_o, rays_d, intrs, c2ws):
+        """ref_gray_val / sampled_gray_val of the 18-key dict (the training extras); the cameras come from the call's
+        arguments, or from the prepared scene when the caller passed a PreparedScene and no matrices."""
+        if intrs is None or c2ws is None:
+            intrs, c2ws = scene.intrs_host, scene.c2ws_host
+        if intrs is None or not scene.has_images:
+            return {}
+        ro = rays_o.detach().to(torch.float32).contiguous()
+        rd = rays_d.detach().to(torch.float32).contiguous()
+        return self._render_extras(t, scene, ro, rd, intrs, c2ws)
+
     def _finish_dict(self, t, scene, B, S, pts_random, device):
         inv_s = self.deviation_network.inv_s().to(device)
         ge = t["gradient_error_sums"]
@@ -259,7 +315,7 @@ class ImplicitSurface(nn.Module):
     # -- reference API -----------------------------------------------------------------------------
     def render_core(self, rays_o, rays_d, z_vals, sample_dist, volumes, sparse_idxes, mask_volumes, features,
                     match_features, imgs, intrs, c2ws, near, far, cos_anneal_ratio, step, pts_random=None,
-                    return_stages=False):
+                    return_stages=False, extras=True):
         """implicit_surface.py:64-266 (inference keys).  ``sample_dist`` must be 2/n_samples[0]."""
         scene = volumes if isinstance(volumes, PreparedScene) else self.prepare(
             None, volumes, sparse_idxes, mask_volumes, imgs, features, intrs, c2ws)
@@ -269,13 +325,16 @@ class ImplicitSurface(nn.Module):
         t = self._render_device(scene, rays_o, rays_d, None, None, None, z_vals, cos_anneal_ratio, 0,
                                 stages=return_stages)
         ret = self._finish_dict(t, scene, B, S, pts_random, rays_o.device)
+        if extras:
+            ret.update(self._extras(t, scene, rays_o, rays_d, intrs, c2ws))
         if return_stages:
             for k in ("point_flags", "point_color", "point_views", "prev_idx", "alpha"):
                 ret["_" + k] = t[k]
         return ret
 
     def render(self, rays_o, rays_d, near, far, matching_volume, volumes, sparse_idxes, mask_volumes, imgs, features,
-               match_features, intrs, c2ws, cos_anneal_ratio, step, t_rand=None, pts_random=None, return_stages=False):
+               match_features, intrs, c2ws, cos_anneal_ratio, step, t_rand=None, pts_random=None, return_stages=False,
+               extras=True):
         """implicit_surface.py:268-335.  With ``t_rand`` / ``pts_random`` = None the random numbers are drawn
         from torch's global CPU generator in the reference's order, so seeding reproduces its sample positions."""
         scene = matching_volume if isinstance(matching_volume, PreparedScene) else self.prepare(
@@ -290,6 +349,8 @@ class ImplicitSurface(nn.Module):
         t = self._render_device(scene, rays_o, rays_d, near, far, t_rand, None, cos_anneal_ratio, 0,
                                 stages=return_stages)
         ret = self._finish_dict(t, scene, B, S, pts_random, rays_o.device)
+        if extras:
+            ret.update(self._extras(t, scene, rays_o, rays_d, intrs, c2ws))
         if return_stages:
             for k in ("point_flags", "point_color", "point_views", "prev_idx", "alpha"):
                 ret["_" + k] = t[k]

@@ -102,6 +102,7 @@ class PreparedScene:
         self.n_src_views = 0
         self.has_matching = matching_volume is not None
         self.has_images = False
+        self.intrs_host = self.c2ws_host = None
         self._view_key = None
         self._vol_versions = [v._version for v in volumes]
         handle = C.c_void_p()
@@ -162,6 +163,7 @@ class PreparedScene:
         self.n_views = v.n_views
         self.n_src_views = max(0, self.n_views - 1)
         self.has_images = self.has_images or imgs is not None
+        self.intrs_host, self.c2ws_host = K_h, c2w_h         # the training extras form their 3x3 matrices from these
         self._view_key = key
         # the key holds ids: keep the objects alive so an id cannot be recycled by another tensor
         self._view_refs = [imgs] + _as_list(features) + [intrs, c2ws]

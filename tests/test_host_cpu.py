@@ -83,12 +83,13 @@ def test_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(_lib.LIB_PATH)
     for name in declared:
         assert hasattr(lib, name), name
-    assert _lib.load().surf_version() == _lib.ABI_VERSION == 2
+    assert _lib.load().surf_version() == _lib.ABI_VERSION == 3
 
 
 def test_struct_sizes_match_header():
     # mirrors of the POD structs: a size drift means the ctypes binding no longer matches the header
-    assert ctypes.sizeof(_lib.RenderOutputs) == 20 * 8
+    assert ctypes.sizeof(_lib.RenderOutputs) == 22 * 8
+    assert ctypes.sizeof(_lib.ExtrasParams) == 4 * (9 + 3 + 9 + 9 + 8 * 9 + 8 * 9 + 8 * 3 + 2)
     assert ctypes.sizeof(_lib.RenderCfg) == 4 + 16 + 16 + 4 + 4 + 4 + 4 + 4 + 8 + 8  # incl. alignment padding
     assert ctypes.sizeof(_lib.SceneStats) == 9 * 8
 

@@ -116,3 +116,21 @@ def test_reference_gradient_moves_with_the_last_bit_of_the_position():
         dev[base] = float(torch.quantile(d, 0.999))
     assert dev[32] > 3 * dev[4], dev                  # 8x the resolution: the sensitivity grows with it
     assert dev[32] > 3e-6, dev                        # already >= 3 % of the 1e-4 budget per ulp at 256^3 (704^3: x2.75)
+
+
+@pytest.mark.parametrize("name", ["render_v2_perturbed", "render_v2_init", "render_v4_perturbed", "render_miss"])
+def test_training_extras_match_the_reference(name):
+    """The training-only outputs of render() (implicit_surface.py:172, 218-245; projector.py:560-645): smooth_error
+    (second-order autograd) and the warped 11x11 feature patches, restated in the oracle, against the reference's own
+    outputs."""
+    g = load_golden(name)
+    sc = scene_from_recipe(g["recipe"])
+    net = O.OracleNet(g["sd"])
+    i = g["in"]
+    torch.manual_seed(int(g["recipe"]["torch_seed"]))
+    out = O.render(net, i["rays_o"], i["rays_d"], i["near"], i["far"], sc.matching_volume, sc.volumes, sc.sparse_idxes,
+                   sc.mask_volumes, sc.imgs, sc.features, sc.intrs, sc.c2ws, 1.0, extras=True)
+    for k in ("ref_gray_val", "sampled_gray_val"):
+        assert out[k].shape == tuple(g["out"][k].shape)
+        assert_close(out[k], g["out"][k], 1e-6, k)
+    assert_close(out["smooth_error"], g["out"]["smooth_error"], 1e-5, "smooth_error")
