@@ -154,10 +154,18 @@ def make_scene(nv=3, H=576, W=800, base=88, seed=1, device="cpu", n_levels=4, fe
             m = _shell_mask(n, parent, base_range * range_ratios[l], device)
         parent = m
         flat = m.reshape(-1)
-        nvox = int(flat.sum())
-        idx = torch.cumsum(flat, 0, dtype=torch.int64)      # in place from here on: 1408^3 int64 is 22 GB
-        idx -= 1
-        idx.masked_fill_(~flat, -1)
+        # running voxel number, in slabs of 2^28 entries (1408^3 = 2.8e9 entries: int64 table of 22 GB, built in place;
+        # single torch reductions / scans over more than 2^31 elements are not reliable)
+        idx = torch.empty(flat.shape[0], dtype=torch.int64, device=device)
+        nvox = 0
+        for a in range(0, flat.shape[0], 1 << 28):
+            f = flat[a:a + (1 << 28)]
+            c = torch.cumsum(f, 0, dtype=torch.int64)
+            c += nvox - 1
+            c.masked_fill_(~f, -1)
+            idx[a:a + (1 << 28)] = c
+            nvox += int(f.sum())
+            del c
         idx = idx.reshape(n, n, n)
         g.manual_seed(seed + 100 + l)
         vol = torch.randn((nvox, feat_ch), generator=g, device=device, dtype=torch.float32) * 0.1
