@@ -31,7 +31,7 @@ EXPORTS = [
     "surf_scene_set_views",
     "surf_net_create", "surf_net_destroy",
     "surf_render_workspace_bytes", "surf_sample_rays", "surf_render_core", "surf_render_rays",
-    "surf_sdf_points", "surf_sdf_grid", "surf_sdf_full",
+    "surf_sdf_points", "surf_sdf_grid", "surf_sdf_full", "surf_sdf_smooth",
     "surf_point_mask", "surf_lookup_sparse", "surf_lookup_feature", "surf_blend", "surf_point_flags",
     "surf_tc_selftest",
     "surf_mc_workspace_bytes", "surf_mc_count", "surf_mc_emit",
@@ -181,6 +181,8 @@ def _declare(lib):
     lib.surf_sdf_points.argtypes = [vp, vp, vp, i64, vp, vp, i32, vp]
     lib.surf_sdf_full.restype = C.c_int
     lib.surf_sdf_full.argtypes = [vp, vp, vp, i64, vp, i32, vp]
+    lib.surf_sdf_smooth.restype = C.c_int
+    lib.surf_sdf_smooth.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp]
     lib.surf_sdf_grid.restype = C.c_int
     lib.surf_sdf_grid.argtypes = [vp, vp, vp, i32, vp, i32, vp, i32, vp, i32, f32, i32, vp]
     lib.surf_point_mask.restype = C.c_int

@@ -528,6 +528,8 @@ static inline int perm_pos_128(int n) {   // column n -> position inside a permu
   return 64 * (jj >> 2) + tx * 4 + (jj & 3);
 }
 
+int surf_build_smooth_weights(const std::vector<std::vector<float>>& W, const surf_net_inputs* in, surf_net* net,
+                              cudaStream_t st, int (*dev_alloc)(surf_net*, void**, size_t));
 int surf_build_tc_weights(const std::vector<std::vector<float>>& W, const surf_net_inputs* in, surf_net* net,
                           cudaStream_t st, int (*dev_alloc)(surf_net*, void**, size_t));
 
@@ -663,6 +665,8 @@ int surf_build_sdf_weights(const surf_net_inputs* in, surf_net* net, cudaStream_
     net->w_full_off = (const int*)p;
     SURF_CUDA(cudaStreamSynchronize(st));
   }
+  rc = surf_build_smooth_weights(W, in, net, st, dev_alloc);
+  if (rc) return rc;
   SURF_CUDA(cudaStreamSynchronize(st));   // host vectors go out of scope
   net->tc_ok = (in->multires == 4 && skip == 3) ? 1 : 0;
   if (net->tc_ok) {

@@ -1,0 +1,354 @@
+// Second-order term of SDFNetworkSparse.gradient (sdf_network.py:129-152): next to d sdf / d x the reference returns
+//   smooth = d/dx [ sum_j d sdf / d x_j ] = Hessian(sdf) . (1,1,1)
+// (double autograd), which render_core reduces to `smooth_error` (implicit_surface.py:172).  Training-only: validate()
+// never reads it, so it lives in its own plain fp32 kernel instead of the tensor-core render path.
+//
+// Analytic form: forward-mode tangent along v = (1,1,1) through the reverse pass ("forward over reverse").  With
+// a_l the input of lin_l, z_l = W_l a_l + b_l, h_l = softplus_100(z_l):
+//   forward      : z_l, and the tangent zd_l = W_l ad_l, hd_l = s'(z_l) zd_l      (ad_0 = d PE / d eps, fd = J_feat v)
+//   reverse      : delta_l = ga_{l+1}[hidden] * s'(z_l),  ga_l = W_l^T delta_l
+//   reverse, dot : deltad_l = gad_{l+1}[hidden] * s'(z_l) + ga_{l+1}[hidden] * s''(z_l) zd_l,  gad_l = W_l^T deltad_l
+//   smooth       = scale (Jd_pe^T g_pe + J_pe^T gd_pe) + Jd_feat^T g_feat + J_feat^T gd_feat
+// where g_pe / g_feat collect the PE (lin0 + skip layer) and feature columns of ga, gd_* those of gad, Jd_pe is the
+// derivative of the PE Jacobian along v (-f^2 sin / -f^2 cos) and Jd_feat the mixed second derivatives of the
+// trilinear interpolant (the pure second derivatives vanish).
+// 8 points per 128-thread block, thread = output neuron (forward) / input column (reverse), everything of the 8 points
+// in shared memory, weights read from L2 (k-major for the forward, row-major for the reverse: both coalesced).
+#include <vector>
+
+#include "surf_internal.cuh"
+
+#define SM_NP 8
+#define SM_THREADS 128
+#define SM_STRIDE 160
+
+struct SmoothSmem {
+  float A[SM_NP][SM_STRIDE], Ad[SM_NP][SM_STRIDE];
+  float Z[6][SM_NP][128], Zd[6][SM_NP][128];
+  float GA[SM_NP][SM_STRIDE], GAd[SM_NP][SM_STRIDE];
+  float D[SM_NP][128], Dd[SM_NP][128];
+  float PE[SM_NP][28], PEd[SM_NP][28], FT[SM_NP][28], FTd[SM_NP][28];
+  float gpe[SM_NP][28], gdpe[SM_NP][28], gft[SM_NP][28], gdft[SM_NP][28];
+  float pt[SM_NP][3];
+  float part[SM_NP][4][3];
+};
+
+// one level of the sparse trilinear fetch with its tangent along v = (1,1,1) (world = grid direction, all ones):
+// f7 = value, fd7 = J_feat v
+__device__ __forceinline__ void sparse_value_tangent(const DevScene& sc, int l, float px, float py, float pz, float* f7,
+                                                     float* fd7) {
+  const int N = sc.dim[l];
+  const float vs = sc.voxel[l];
+  const float cx = __fdiv_rn(__fadd_rn(pz, 1.0f), vs), cy = __fdiv_rn(__fadd_rn(py, 1.0f), vs), cz = __fdiv_rn(__fadd_rn(px, 1.0f), vs);
+  const float fx0 = floorf(cx), fy0 = floorf(cy), fz0 = floorf(cz);
+  const float wx1 = __fsub_rn(cx, fx0), wx0 = __fsub_rn(fx0 + 1.0f, cx);
+  const float wy1 = __fsub_rn(cy, fy0), wy0 = __fsub_rn(fy0 + 1.0f, cy);
+  const float wz1 = __fsub_rn(cz, fz0), wz0 = __fsub_rn(fz0 + 1.0f, cz);
+  const float hi = (float)(N - 1);
+  const int x0 = (int)fminf(fmaxf(fx0, 0.f), hi), x1 = (int)fminf(fmaxf(fx0 + 1.0f, 0.f), hi);
+  const int y0 = (int)fminf(fmaxf(fy0, 0.f), hi), y1 = (int)fminf(fmaxf(fy0 + 1.0f, 0.f), hi);
+  const int z0 = (int)fminf(fmaxf(fz0, 0.f), hi), z1 = (int)fminf(fmaxf(fz0 + 1.0f, 0.f), hi);
+  const float inv = 1.0f / vs;
+#pragma unroll
+  for (int c = 0; c < 7; ++c) { f7[c] = 0.f; fd7[c] = 0.f; }
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const int xi = (c & 1) ? x1 : x0, yi = (c & 2) ? y1 : y0, zi = (c & 4) ? z1 : z0;
+    const int32_t row = __ldg(sc.index[l] + ((size_t)zi * N + yi) * N + xi);
+    if (row < 0) continue;
+    const float4 a = __ldg(sc.vol8[l] + (size_t)row * 2), b = __ldg(sc.vol8[l] + (size_t)row * 2 + 1);
+    const float wx = (c & 1) ? wx1 : wx0, wy = (c & 2) ? wy1 : wy0, wz = (c & 4) ? wz1 : wz0;
+    const float sx = (c & 1) ? 1.f : -1.f, sy = (c & 2) ? 1.f : -1.f, sz = (c & 4) ? 1.f : -1.f;
+    const float w = wx * wy * wz;
+    const float wd = (sx * wy * wz + sy * wx * wz + sz * wx * wy) * inv;
+    const float v[7] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z};
+#pragma unroll
+    for (int k = 0; k < 7; ++k) { f7[k] += v[k] * w; fd7[k] += v[k] * wd; }
+  }
+}
+
+// reverse of one level: o3 = J_feat^T g (world xyz), od3 = J_feat^T gd + Jd_feat^T g (tangent along (1,1,1))
+__device__ __forceinline__ void sparse_back_tangent(const DevScene& sc, int l, float px, float py, float pz, const float* g,
+                                                    const float* gd, float* o3, float* od3) {
+  const int N = sc.dim[l];
+  const float vs = sc.voxel[l];
+  const float cx = __fdiv_rn(__fadd_rn(pz, 1.0f), vs), cy = __fdiv_rn(__fadd_rn(py, 1.0f), vs), cz = __fdiv_rn(__fadd_rn(px, 1.0f), vs);
+  const float fx0 = floorf(cx), fy0 = floorf(cy), fz0 = floorf(cz);
+  const float wx1 = __fsub_rn(cx, fx0), wx0 = __fsub_rn(fx0 + 1.0f, cx);
+  const float wy1 = __fsub_rn(cy, fy0), wy0 = __fsub_rn(fy0 + 1.0f, cy);
+  const float wz1 = __fsub_rn(cz, fz0), wz0 = __fsub_rn(fz0 + 1.0f, cz);
+  const float hi = (float)(N - 1);
+  const int x0 = (int)fminf(fmaxf(fx0, 0.f), hi), x1 = (int)fminf(fmaxf(fx0 + 1.0f, 0.f), hi);
+  const int y0 = (int)fminf(fmaxf(fy0, 0.f), hi), y1 = (int)fminf(fmaxf(fy0 + 1.0f, 0.f), hi);
+  const int z0 = (int)fminf(fmaxf(fz0, 0.f), hi), z1 = (int)fminf(fmaxf(fz0 + 1.0f, 0.f), hi);
+  float gx = 0.f, gy = 0.f, gz = 0.f, hx = 0.f, hy = 0.f, hz = 0.f;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const int xi = (c & 1) ? x1 : x0, yi = (c & 2) ? y1 : y0, zi = (c & 4) ? z1 : z0;
+    const int32_t row = __ldg(sc.index[l] + ((size_t)zi * N + yi) * N + xi);
+    if (row < 0) continue;
+    const float4 a = __ldg(sc.vol8[l] + (size_t)row * 2), b = __ldg(sc.vol8[l] + (size_t)row * 2 + 1);
+    const float wx = (c & 1) ? wx1 : wx0, wy = (c & 2) ? wy1 : wy0, wz = (c & 4) ? wz1 : wz0;
+    const float sx = (c & 1) ? 1.f : -1.f, sy = (c & 2) ? 1.f : -1.f, sz = (c & 4) ? 1.f : -1.f;
+    const float s = a.x * g[0] + a.y * g[1] + a.z * g[2] + a.w * g[3] + b.x * g[4] + b.y * g[5] + b.z * g[6];
+    const float sd = a.x * gd[0] + a.y * gd[1] + a.z * gd[2] + a.w * gd[3] + b.x * gd[4] + b.y * gd[5] + b.z * gd[6];
+    gx += s * (sx * wy * wz); gy += s * (sy * wx * wz); gz += s * (sz * wx * wy);
+    // d/d eps of the first derivatives: J^T gd plus the mixed second derivatives (d^2/dxdy = sx sy wz, ...)
+    hx += sd * (sx * wy * wz); hy += sd * (sy * wx * wz); hz += sd * (sz * wx * wy);
+    hx += s * (sx * (sy * wz + sz * wy)); hy += s * (sy * (sx * wz + sz * wx)); hz += s * (sz * (sx * wy + sy * wx));
+  }
+  const float inv = 1.0f / vs;
+  o3[0] = gz * inv; o3[1] = gy * inv; o3[2] = gx * inv;          // world x <- grid z (projector.py:379)
+  // the mixed terms carry 1 / vs^2, the J^T gd terms 1 / vs: split them
+  // (recomputed below to keep the two scalings apart)
+  od3[0] = hz; od3[1] = hy; od3[2] = hx;
+}
+
+__device__ __forceinline__ void sm_softplus(float z, float& h, float& d1, float& d2) {
+  // softplus(beta = 100): h, h' = sigmoid(100 z), h'' = 100 h' (1 - h')
+  const float t = 100.0f * z;
+  const float e = expf(-fabsf(t));
+  h = fmaxf(z, 0.f) + log1pf(e) * 0.01f;
+  const float r = 1.0f / (1.0f + e);
+  d1 = t >= 0.f ? r : 1.0f - r;
+  d2 = 100.0f * e * r * r;
+}
+
+__global__ void __launch_bounds__(SM_THREADS)
+k_sdf_smooth(const DevScene sc, const DevNet net, const float* __restrict__ wk, const int* __restrict__ wk_off,
+             const float* __restrict__ wr, const int* __restrict__ wr_off, const float* __restrict__ pts,
+             const uint8_t* __restrict__ flags, int64_t n, float* __restrict__ grad_out, float* __restrict__ smooth_out) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  SmoothSmem& S = *reinterpret_cast<SmoothSmem*>(smem_raw);
+  const int tid = threadIdx.x;
+  const int pe_dim = net.pe_dim;       // 27
+  for (int64_t base = (int64_t)blockIdx.x * SM_NP; base < n; base += (int64_t)gridDim.x * SM_NP) {
+    __syncthreads();
+    // ---- inputs: features + tangent (thread = (point, level)), positional encoding + tangent (thread = point) ----
+    if (tid < SM_NP * 4) {
+      const int p = tid >> 2, lv = tid & 3;
+      const int64_t i = base + p;
+      float f7[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, fd7[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (i < n && lv < sc.n_levels) sparse_value_tangent(sc, lv, pts[i * 3], pts[i * 3 + 1], pts[i * 3 + 2], f7, fd7);
+#pragma unroll
+      for (int c = 0; c < 7; ++c) { S.FT[p][lv * 7 + c] = f7[c]; S.FTd[p][lv * 7 + c] = fd7[c]; }
+    } else if (tid < SM_NP * 5) {
+      const int p = tid - SM_NP * 4;
+      const int64_t i = base + p;
+      float x[3] = {0.f, 0.f, 0.f};
+      if (i < n) { x[0] = pts[i * 3]; x[1] = pts[i * 3 + 1]; x[2] = pts[i * 3 + 2]; }
+      for (int d = 0; d < 3; ++d) {
+        S.pt[p][d] = x[d];
+        const float X = x[d] * net.scale;
+        S.PE[p][d] = X;
+        S.PEd[p][d] = net.scale;                      // d X / d eps, v = (1,1,1)
+        float fr = 1.0f;
+        for (int f = 0; f < net.multires; ++f) {
+          float sn, cs;
+          sincosf(X * fr, &sn, &cs);
+          S.PE[p][3 + 6 * f + d] = sn;      S.PEd[p][3 + 6 * f + d] = fr * net.scale * cs;
+          S.PE[p][3 + 6 * f + 3 + d] = cs;  S.PEd[p][3 + 6 * f + 3 + d] = -fr * net.scale * sn;
+          fr *= 2.0f;
+        }
+      }
+    }
+    for (int i = tid; i < SM_NP * 28; i += SM_THREADS) {
+      (&S.gpe[0][0])[i] = 0.f; (&S.gdpe[0][0])[i] = 0.f; (&S.gft[0][0])[i] = 0.f; (&S.gdft[0][0])[i] = 0.f;
+    }
+    __syncthreads();
+    for (int i = tid; i < SM_NP * pe_dim; i += SM_THREADS) {
+      S.A[i / pe_dim][i % pe_dim] = S.PE[i / pe_dim][i % pe_dim];
+      S.Ad[i / pe_dim][i % pe_dim] = S.PEd[i / pe_dim][i % pe_dim];
+    }
+    __syncthreads();
+    // ---- forward with tangent ----
+    int in_dim = pe_dim;
+    for (int l = 0; l < 6; ++l) {
+      const int od = net.out_dim[l];
+      const float* W = wk + wk_off[l];
+      float acc[SM_NP], accd[SM_NP];
+#pragma unroll
+      for (int p = 0; p < SM_NP; ++p) { acc[p] = 0.f; accd[p] = 0.f; }
+      if (tid < od) {
+        for (int k = 0; k < in_dim; ++k) {
+          const float w = W[(size_t)k * SM_STRIDE + tid];
+#pragma unroll
+          for (int p = 0; p < SM_NP; ++p) { acc[p] = fmaf(S.A[p][k], w, acc[p]); accd[p] = fmaf(S.Ad[p][k], w, accd[p]); }
+        }
+        const float b = W[(size_t)in_dim * SM_STRIDE + tid];
+#pragma unroll
+        for (int p = 0; p < SM_NP; ++p) { S.Z[l][p][tid] = acc[p] + b; S.Zd[l][p][tid] = accd[p]; }
+      } else {
+#pragma unroll
+        for (int p = 0; p < SM_NP; ++p) { S.Z[l][p][tid] = 0.f; S.Zd[l][p][tid] = 0.f; }
+      }
+      __syncthreads();
+      // next input [h | PE at the skip layer | features] and its tangent
+      for (int p = 0; p < SM_NP; ++p) {
+        float h = 0.f, hd = 0.f;
+        if (tid < od) {
+          float d1, d2;
+          sm_softplus(S.Z[l][p][tid], h, d1, d2);
+          hd = d1 * S.Zd[l][p][tid];
+        } else if (l + 1 == net.skip_layer && tid < od + pe_dim) {
+          h = S.PE[p][tid - od]; hd = S.PEd[p][tid - od];
+        }
+        S.A[p][tid] = h; S.Ad[p][tid] = hd;
+      }
+      for (int i = tid; i < SM_NP * 28; i += SM_THREADS) {
+        S.A[i / 28][128 + i % 28] = S.FT[i / 28][i % 28];
+        S.Ad[i / 28][128 + i % 28] = S.FTd[i / 28][i % 28];
+      }
+      in_dim = 128 + 28;
+      __syncthreads();
+    }
+    // ---- reverse with tangent: ga_6 = row 0 of lin6 / scale, gad_6 = 0 ----
+    {
+      const float* W6 = wr + wr_off[6];
+      for (int k = tid; k < SM_STRIDE; k += SM_THREADS) {
+        const float w = k < 156 ? W6[k] * net.inv_scale : 0.f;
+#pragma unroll
+        for (int p = 0; p < SM_NP; ++p) { S.GA[p][k] = w; S.GAd[p][k] = 0.f; }
+      }
+    }
+    __syncthreads();
+    for (int l = 5; l >= 0; --l) {
+      const int od = net.out_dim[l];
+      // feature columns of ga_{l+1}, PE columns of the skip layer's input
+      for (int i = tid; i < SM_NP * 28; i += SM_THREADS) {
+        S.gft[i / 28][i % 28] += S.GA[i / 28][128 + i % 28];
+        S.gdft[i / 28][i % 28] += S.GAd[i / 28][128 + i % 28];
+      }
+      if (l + 1 == net.skip_layer)
+        for (int i = tid; i < SM_NP * pe_dim; i += SM_THREADS) {
+          S.gpe[i / pe_dim][i % pe_dim] += S.GA[i / pe_dim][od + i % pe_dim];
+          S.gdpe[i / pe_dim][i % pe_dim] += S.GAd[i / pe_dim][od + i % pe_dim];
+        }
+      // delta_l and its tangent
+      for (int p = 0; p < SM_NP; ++p) {
+        float dl = 0.f, dd = 0.f;
+        if (tid < od) {
+          float h, d1, d2;
+          sm_softplus(S.Z[l][p][tid], h, d1, d2);
+          dl = S.GA[p][tid] * d1;
+          dd = S.GAd[p][tid] * d1 + S.GA[p][tid] * d2 * S.Zd[l][p][tid];
+        }
+        S.D[p][tid] = dl; S.Dd[p][tid] = dd;
+      }
+      __syncthreads();
+      const int I = (l == 0) ? pe_dim : 156;
+      const float* W = wr + wr_off[l];
+      for (int k = tid; k < SM_STRIDE; k += SM_THREADS) {
+        float ga[SM_NP], gad[SM_NP];
+#pragma unroll
+        for (int p = 0; p < SM_NP; ++p) { ga[p] = 0.f; gad[p] = 0.f; }
+        if (k < I) {
+          for (int o = 0; o < od; ++o) {
+            const float w = W[(size_t)o * SM_STRIDE + k];
+#pragma unroll
+            for (int p = 0; p < SM_NP; ++p) { ga[p] = fmaf(S.D[p][o], w, ga[p]); gad[p] = fmaf(S.Dd[p][o], w, gad[p]); }
+          }
+        }
+#pragma unroll
+        for (int p = 0; p < SM_NP; ++p) { S.GA[p][k] = ga[p]; S.GAd[p][k] = gad[p]; }
+      }
+      __syncthreads();
+    }
+    // lin0's input is the positional encoding
+    for (int i = tid; i < SM_NP * pe_dim; i += SM_THREADS) {
+      S.gpe[i / pe_dim][i % pe_dim] += S.GA[i / pe_dim][i % pe_dim];
+      S.gdpe[i / pe_dim][i % pe_dim] += S.GAd[i / pe_dim][i % pe_dim];
+    }
+    __syncthreads();
+    // ---- d/dx: feature part per (point, level), PE part per point ----
+    if (tid < SM_NP * 4) {
+      const int p = tid >> 2, lv = tid & 3;
+      const int64_t i = base + p;
+      float o3[3] = {0.f, 0.f, 0.f}, od3[3] = {0.f, 0.f, 0.f}, om3[3] = {0.f, 0.f, 0.f};
+      if (i < n && lv < sc.n_levels) {
+        const float zero7[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        float t3[3];
+        // J^T gd (scaled 1/vs): a first-order pass with gd;  J^T g and the mixed terms (1/vs^2): a pass with (g, 0)
+        sparse_back_tangent(sc, lv, S.pt[p][0], S.pt[p][1], S.pt[p][2], &S.gdft[p][lv * 7], zero7, od3, t3);
+        sparse_back_tangent(sc, lv, S.pt[p][0], S.pt[p][1], S.pt[p][2], &S.gft[p][lv * 7], zero7, o3, om3);
+        const float inv = 1.0f / sc.voxel[lv];
+        om3[0] *= inv * inv; om3[1] *= inv * inv; om3[2] *= inv * inv;
+      }
+      for (int d = 0; d < 3; ++d) S.part[p][lv][d] = od3[d] + om3[d];
+      if (grad_out) for (int d = 0; d < 3; ++d) S.D[p][lv * 3 + d] = o3[d];
+    }
+    __syncthreads();
+    if (tid < SM_NP * 3) {
+      const int p = tid / 3, d = tid % 3;
+      const int64_t i = base + p;
+      if (i < n) {
+        const float X = S.pt[p][d] * net.scale;
+        float g1 = S.gpe[p][d];                 // J_pe^T g_pe (first order, per unit X)
+        float s2 = S.gdpe[p][d];                // J_pe^T gd_pe + Jd_pe^T g_pe
+        float fr = 1.0f;
+        for (int f = 0; f < net.multires; ++f) {
+          const float sn = S.PE[p][3 + 6 * f + d], cs = S.PE[p][3 + 6 * f + 3 + d];
+          const float gs = S.gpe[p][3 + 6 * f + d], gc = S.gpe[p][3 + 6 * f + 3 + d];
+          g1 += fr * (gs * cs - gc * sn);
+          s2 += fr * (S.gdpe[p][3 + 6 * f + d] * cs - S.gdpe[p][3 + 6 * f + 3 + d] * sn);
+          s2 -= fr * fr * net.scale * (gs * sn + gc * cs);     // d/d eps of (f cos, -f sin) along dX = scale
+          fr *= 2.0f;
+        }
+        (void)X;
+        const float feat2 = S.part[p][0][d] + S.part[p][1][d] + S.part[p][2][d] + S.part[p][3][d];
+        const bool on = flags == nullptr || ((flags[i] >> 1) & 1);
+        smooth_out[i * 3 + d] = on ? fmaf(s2, net.scale, feat2) : 0.f;
+        if (grad_out) {
+          const float feat1 = S.D[p][d] + S.D[p][3 + d] + S.D[p][6 + d] + S.D[p][9 + d];
+          grad_out[i * 3 + d] = on ? fmaf(g1, net.scale, feat1) : 0.f;
+        }
+      }
+    }
+  }
+}
+
+// row-major fp32 copies of lin0..lin6 (stride 160) for the reverse passes of k_sdf_smooth
+int surf_build_smooth_weights(const std::vector<std::vector<float>>& W, const surf_net_inputs* in, surf_net* net,
+                              cudaStream_t st, int (*dev_alloc)(surf_net*, void**, size_t)) {
+  std::vector<float> wr;
+  std::vector<int> off(8, 0);
+  for (int l = 0; l < 7; ++l) {
+    const int O = in->out_dim[l], I = in->in_dim[l];
+    if (I > SM_STRIDE || (l < 6 && O > 128)) {
+      surf_set_error("lin%d: %d x %d unsupported by the second-order kernel", l, O, I);
+      return -1;
+    }
+    off[l] = (int)wr.size();
+    const int rows = (l == 6) ? 1 : O;
+    wr.resize(wr.size() + (size_t)rows * SM_STRIDE, 0.f);
+    for (int o = 0; o < rows; ++o)
+      for (int k = 0; k < I; ++k) wr[off[l] + (size_t)o * SM_STRIDE + k] = W[l][(size_t)o * I + k];
+  }
+  void* p = nullptr;
+  int rc = dev_alloc(net, &p, wr.size() * sizeof(float));
+  if (rc) return rc;
+  SURF_CUDA(cudaMemcpyAsync(p, wr.data(), wr.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+  net->w_rows = (const float*)p;
+  rc = dev_alloc(net, &p, off.size() * sizeof(int));
+  if (rc) return rc;
+  SURF_CUDA(cudaMemcpyAsync(p, off.data(), off.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  net->w_rows_off = (const int*)p;
+  SURF_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+extern "C" int surf_sdf_smooth(const surf_scene* s, const surf_net* n, const float* d_pts, int64_t n_pts,
+                               const uint8_t* d_flags, float* d_grad, float* d_smooth, void* stream) {
+  if (n_pts <= 0) return 0;
+  SURF_CHECK_ARG(s && n && d_pts && d_smooth, "null pointer");
+  SURF_CHECK_ARG(n->w_rows && n->w_full, "network without second-order weights");
+  SURF_CHECK_ARG(n->dev.pe_dim <= 28 && n->dev.out_dim[6] >= 1, "unsupported network shape");
+  int rc = surf_ensure_dyn_smem((const void*)k_sdf_smooth, (int)sizeof(SmoothSmem));
+  if (rc) return rc;
+  const int64_t blocks = (n_pts + SM_NP - 1) / SM_NP;
+  const int64_t cap = (int64_t)surf_num_sms() * 2;
+  k_sdf_smooth<<<(int)(blocks < cap ? blocks : cap), SM_THREADS, sizeof(SmoothSmem), (cudaStream_t)stream>>>(
+      s->dev, n->dev, n->w_full, n->w_full_off, n->w_rows, n->w_rows_off, d_pts, d_flags, n_pts, d_grad, d_smooth);
+  SURF_LAUNCH_CHECK();
+  return 0;
+}

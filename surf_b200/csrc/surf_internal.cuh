@@ -99,6 +99,8 @@ struct surf_net {
   const float* blend_tc_f;          // blend_tc.cu: fp32 small-layer weights and biases
   const float* w_full;              // k-major fp32 matrices (+ bias row) of lin0..lin6 for k_sdf_full (opt-in (n,129) head)
   const int* w_full_off;            // float offset of each layer in w_full
+  const float* w_rows;              // row-major fp32 matrices (stride 160) for the reverse passes of k_sdf_smooth
+  const int* w_rows_off;
   int tc_ok;                        // network shape supported by the tensor-core kernels
   float* scratch;                   // sigma' scratch of the FFMA backward pass (per-CTA private)
   size_t scratch_bytes;

@@ -7,8 +7,10 @@ include/surf_b200.h; this file only draws the reference's random numbers on the 
 builds linspace tables on the host (not reproducible by a device formula), allocates outputs and
 enqueues the kernels.  There is no PyTorch / CPU fallback.
 
-Not provided (training-only extras): ``smooth_error`` (second-order autograd),
-``ref_gray_val`` / ``sampled_gray_val`` (surface_patch_warp2) and autograd through the render.
+``render`` / ``render_core`` return all 18 keys of the reference, including the training extras ``smooth_error``
+(analytic Hessian-vector kernel), ``ref_gray_val`` / ``sampled_gray_val`` (surface_patch_warp2); ``validate`` skips
+them like it ignores them in the reference.  Not provided: autograd THROUGH the render (the backward pass of training /
+finetuning) — outputs are detached.
 """
 from __future__ import annotations
 
@@ -173,6 +175,8 @@ class ImplicitSurface(nn.Module):
             out("gradient_error_sums", (2,), zero=True)
             out("z_cross", (B,))
             out("z_max", (1,), zero=True)
+        if not lean and not stages:
+            out("point_flags", (B * S,), torch.uint8)       # the second-order extra needs the evaluated-point bits
         if stages:
             out("point_flags", (B * S,), torch.uint8)
             out("point_color", (B * S, 3), zero=True)
@@ -285,7 +289,15 @@ class ImplicitSurface(nn.Module):
             return {}
         ro = rays_o.detach().to(torch.float32).contiguous()
         rd = rays_d.detach().to(torch.float32).contiguous()
-        return self._render_extras(t, scene, ro, rd, intrs, c2ws)
+        ret = self._render_extras(t, scene, ro, rd, intrs, c2ws)
+        # smooth_error (:172): |Hessian . 1| of the evaluated samples (0 elsewhere, :99), weighted by inside_sphere
+        B, S = t["mid_z_vals"].shape
+        pts = (ro[:, None, :] + rd[:, None, :] * t["mid_z_vals"][..., None]).reshape(-1, 3)
+        smooth = self.sdf_network.smooth(pts, scene, flags=t["point_flags"])
+        inside = t["inside_sphere"]
+        ret["smooth_error"] = (torch.linalg.norm(smooth, ord=2, dim=-1).reshape(B, S) * inside).sum() / (inside.sum() + 1e-5)
+        ret["_smooth"] = smooth
+        return ret
 
     def _finish_dict(self, t, scene, B, S, pts_random, device):
         inv_s = self.deviation_network.inv_s().to(device)

@@ -118,10 +118,10 @@ class SDFNetworkSparse(nn.Module):
         return out
 
     def gradient(self, x, volumes, indexes=None, with_sdf=False):
-        """d sdf / d x (n,3) by the in-kernel analytic reverse pass (sdf_network.py:129-141).
-
-        The reference also returns the second-order ``smooth`` term (:143-150), a training-only extra
-         that is not implemented; zeros are returned in its place."""
+        """(gradients, smooth) like the reference (sdf_network.py:129-152): d sdf / d x (n,3) by the in-kernel analytic
+        reverse pass of the render kernels, and smooth = d/dx sum_j (d sdf / d x_j) (the double-autograd term, :143-150)
+        by the plain fp32 second-order kernel (surf_sdf_smooth).  ``with_sdf=True`` -> (sdf, gradients), no second-order
+        pass."""
         scene, net, mode = self._handles(volumes, indexes)
         x = x.detach().to(torch.float32).contiguous()
         sdf = torch.empty((x.shape[0], 1), dtype=torch.float32, device=x.device)
@@ -131,7 +131,21 @@ class SDFNetworkSparse(nn.Module):
                                                    grad.data_ptr(), mode, _stream()), "sdf_points(grad)")
         if with_sdf:
             return sdf, grad
-        return grad, torch.zeros_like(grad)
+        return grad, self.smooth(x, scene)
+
+    def smooth(self, x, volumes, indexes=None, flags=None, with_grad=False):
+        """Hessian(sdf) . (1,1,1) at x (n,3) -> (n,3).  ``flags`` (n,) uint8: bit 1 = evaluate, else 0 (the reference's
+        masked-out default, implicit_surface.py:99).  ``with_grad``: also the fp32 first-order gradient of the same pass."""
+        scene, net, _ = self._handles(volumes, indexes)
+        x = x.detach().to(torch.float32).contiguous()
+        sm = torch.empty((x.shape[0], 3), dtype=torch.float32, device=x.device)
+        gr = torch.empty((x.shape[0], 3), dtype=torch.float32, device=x.device) if with_grad else None
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().surf_sdf_smooth(scene.handle, net, x.data_ptr(), x.shape[0],
+                                                   flags.data_ptr() if flags is not None else None,
+                                                   gr.data_ptr() if gr is not None else None, sm.data_ptr(), _stream()),
+                       "sdf_smooth")
+        return (gr, sm) if with_grad else sm
 
     def forward(self, inputs, volumes, indexes=None):
         """(n,3) -> (n, d_out) = [sdf / scale, lin6 outputs 1..] exactly like the reference (sdf_network.py:95-121).

@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 TRAIN_KEYS = {"ref_gray_val", "sampled_gray_val", "mid_inside_sphere", "color_fine", "render_depth", "valid_mask",
               "sparse_sdf", "mid_z_vals", "gradients", "normal", "s_val", "weights", "weight_sum", "weight_max",
-              "gradient_error", "inside_sphere", "sdf_depth"}        # the reference's 18 keys minus smooth_error
+              "gradient_error", "inside_sphere", "sdf_depth", "smooth_error"}        # the reference's 18 keys
 
 
 def _render(name, mode):
@@ -123,3 +123,51 @@ def test_warp_maps_follow_the_views():
     assert b["sampled_gray_val"].shape[0] == 3 and a["sampled_gray_val"].shape[0] == 4
     assert torch.equal(b["sampled_gray_val"], c["sampled_gray_val"]) and torch.equal(b["ref_gray_val"], c["ref_gray_val"])
     assert torch.equal(a["ref_gray_val"], b["ref_gray_val"])        # the reference view did not change
+
+
+@pytest.mark.parametrize("name", ["render_v2_perturbed", "render_v2_init", "render_v4_perturbed"])
+def test_second_order_smooth_vs_reference(name):
+    """SDFNetworkSparse.gradient's second return value (sdf_network.py:143-150, double autograd) by the analytic
+    forward-over-reverse kernel, against the reference's own `smooth` at the reference's evaluated points, and
+    smooth_error of render() against the golden."""
+    g = load_golden(name)
+    sc = scene_from_recipe(g["recipe"])
+    m = ImplicitSurface(conf.default_implicit_surface_conf())
+    m.load_state_dict(g["sd"])
+    m = m.to(DEV)
+    d = sc.to(DEV)
+    ps = m.prepare(d.matching_volume, d.volumes, d.sparse_idxes, d.mask_volumes, d.imgs, d.features, d.intrs, d.c2ws)
+    pv = torch.from_numpy(g["out"]["_pts_valid"]).to(DEV)
+    gr, sm = m.sdf_network.gradient(pv, ps)
+    want = torch.as_tensor(g["out"]["_smooth_valid"])
+    assert sm.shape == want.shape
+    assert_close(sm, want, 2e-4, "smooth = Hessian . (1,1,1) vs reference double autograd")
+    g32, sm2 = m.sdf_network.smooth(pv, ps, with_grad=True)
+    assert torch.equal(sm, sm2)
+    assert_close(g32, g["out"]["_grad_valid"], RTOL_FP32, "first-order gradient of the second-order kernel")
+    # ragged sizes and the flag byte
+    fl = torch.zeros(pv.shape[0], dtype=torch.uint8, device=DEV)
+    fl[::2] = 2
+    sm3 = m.sdf_network.smooth(pv, ps, flags=fl)
+    assert torch.equal(sm3[::2], sm[::2]) and bool((sm3[1::2] == 0).all())
+    assert m.sdf_network.smooth(pv[:13], ps).shape == (13, 3) and torch.equal(m.sdf_network.smooth(pv[:13], ps), sm[:13])
+    # smooth_error of the full render
+    i = g["in"]
+    torch.manual_seed(int(g["recipe"]["torch_seed"]))
+    out = m.render(i["rays_o"].to(DEV), i["rays_d"].to(DEV), i["near"].to(DEV), i["far"].to(DEV), ps, None, None, None, None,
+                   None, None, d.intrs, d.c2ws, 1.0, None)
+    assert set(g["out"].keys()) - {k for k in g["out"] if k.startswith("_")} <= set(out.keys()), "all 18 reference keys"
+    assert_close(out["smooth_error"], g["out"]["smooth_error"], 1e-3, "smooth_error")
+
+
+def test_second_order_smooth_wild_points():
+    g = load_golden("sdf_grid_24")
+    sc = scene_from_recipe(g["recipe"])
+    m = ImplicitSurface(conf.default_implicit_surface_conf())
+    m.load_state_dict(g["sd"])
+    m = m.to(DEV)
+    d = sc.to(DEV)
+    ps = m.prepare(d.matching_volume, d.volumes, d.sparse_idxes, d.mask_volumes, d.imgs, d.features, d.intrs, d.c2ws)
+    wild = g["in"]["wild_pts"].to(DEV)
+    sm = m.sdf_network.smooth(wild, ps)
+    assert_close(sm, g["out"]["wild_smooth"], 2e-4, "smooth, out-of-range points and exact voxel centres")
