@@ -123,7 +123,16 @@ k_sdf_smooth(const DevScene sc, const DevNet net, const float* __restrict__ wk, 
   const int tid = threadIdx.x;
   const int pe_dim = net.pe_dim;       // 27
   for (int64_t base = (int64_t)blockIdx.x * SM_NP; base < n; base += (int64_t)gridDim.x * SM_NP) {
-    __syncthreads();
+    // a group of points none of which is evaluated (masked-out samples of a ray): zeros, no work
+    int live = (flags == nullptr) ? 1 : 0;
+    if (flags != nullptr && tid < SM_NP && base + tid < n) live = (flags[base + tid] >> 1) & 1;
+    if (!__syncthreads_or(live)) {
+      if (tid < SM_NP * 3 && base + tid / 3 < n) {
+        smooth_out[(base + tid / 3) * 3 + tid % 3] = 0.f;
+        if (grad_out) grad_out[(base + tid / 3) * 3 + tid % 3] = 0.f;
+      }
+      continue;
+    }
     // ---- inputs: features + tangent (thread = (point, level)), positional encoding + tangent (thread = point) ----
     if (tid < SM_NP * 4) {
       const int p = tid >> 2, lv = tid & 3;
