@@ -104,18 +104,31 @@ __device__ __forceinline__ float t2_rcp(float x) {
 }
 // softplus(beta = 100), branch-free: max(z, 0) + log1p(e) / 100 with e = exp(-|100 z|) in (0, 1].
 // softplus'(z) = sigmoid(100 z) = z >= 0 ? 1 / (1 + e) : 1 - 1 / (1 + e).  For the reverse pass the forward epilogue
-// parks e as a 16-bit fixed-point code plus the sign of z (no F2I: min(e, 1 - 2^-16) + 128.0f has ulp 2^-16, the
-// adder's round-to-nearest leaves round(e * 65536) in the low 16 bits of the word).
+// parks e as fp16 (two per word, one F2FP per pair) plus the sign of z in a separate bit word.
 __device__ __forceinline__ float t2_softplus(float z, float& e) {
   e = t2_ex2(fabsf(z) * -144.26950408889634f);
   return fmaf(t2_lg2(1.0f + e), 0.0069314718055994531f, fmaxf(z, 0.f));
 }
-__device__ __forceinline__ uint32_t t2_code_word(float e) { return __float_as_uint(fminf(e, 0.9999847412109375f) + 128.0f); }
-// pair word (two codes) -> u = 1 + e of element t
+// pair word: e of two elements as fp16.  The error of softplus' = 1 / (1 + e) is <= e 2^-12 / (1 + e)^2 <= 6e-5 and is
+// that large only for the few units with |100 z| < ~3; (round 1 used a 16-bit fixed-point code: two more instructions per
+// activation in an issue-bound epilogue).  t2_decode_u: u = 1 + e of element T.
+__device__ __forceinline__ uint32_t t2_code_pair(float e0, float e1) {
+  const __half2 h = __floats2half2_rn(e0, e1);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
 template <int T>
 __device__ __forceinline__ float t2_decode_u(uint32_t pair) {
-  return __uint_as_float(__byte_perm(pair, 0x43000000u, T ? 0x7632 : 0x7610)) - 127.0f;
+  const __half2 h = *reinterpret_cast<const __half2*>(&pair);
+  return (T ? __high2float(h) : __low2float(h)) + 1.0f;
 }
+
+// The timing-experiment switches (flag bits 4 no MMAs, 8 no activation math, 16 no code scratch, 32 no weight traffic,
+// 64 no gathers) exist only in a -DT2_DEBUG build; in the product library they are compile-time false.
+#ifdef T2_DEBUG
+#define T2_DBG(word, bit) (((word) & (bit)) != 0)
+#else
+#define T2_DBG(word, bit) false
+#endif
 
 struct T2Epi {
   uint32_t tl;            // TMEM base of my lane quarter
@@ -126,7 +139,7 @@ struct T2Epi {
   uint4* scratch;
   uint32_t* sgn_scratch;
   float* s_gpe;
-  int dbg;                // timing experiments (SURF_T2_DEBUG): 8 = skip the activation math, 16 = skip the code scratch
+  int dbg;                // timing experiments (only in a -DT2_DEBUG build): 8 = skip the activation math, 16 = skip the code scratch
 };
 
 __device__ __forceinline__ float t2_get_k(const uint8_t* base, int r, int k) {
@@ -141,7 +154,7 @@ __device__ __forceinline__ float t2_get_k(const uint8_t* base, int r, int k) {
 template <bool GRAD, int SKIP, bool HEAD>
 __device__ __forceinline__ void t2_fwd_act(const T2Epi& c, int cb, const uint32_t (&d)[8], float (&h)[8], uint4& spw,
                                            uint32_t& sgn, float& head) {
-  uint32_t cw[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+  float cw[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
   for (int n = 0; n < 8; ++n) {
     const bool pe = (SKIP == 2) || (SKIP == 1 && n >= 5);
@@ -160,14 +173,14 @@ __device__ __forceinline__ void t2_fwd_act(const T2Epi& c, int cb, const uint32_
           h[n] = w * c.inv_scale * (z >= 0.f ? rr : 1.0f - rr);
         }
       } else if (GRAD) {
-        cw[n] = t2_code_word(e);
+        cw[n] = e;
         sgn = __funnelshift_l(__float_as_uint(z), sgn, 1);      // element e of the layer ends at bit 31 - e
       }
     }
   }
   if (GRAD && !HEAD)
-    spw = make_uint4(__byte_perm(cw[0], cw[1], 0x5410), __byte_perm(cw[2], cw[3], 0x5410), __byte_perm(cw[4], cw[5], 0x5410),
-                     __byte_perm(cw[6], cw[7], 0x5410));
+    spw = make_uint4(t2_code_pair(cw[0], cw[1]), t2_code_pair(cw[2], cw[3]), t2_code_pair(cw[4], cw[5]),
+                     t2_code_pair(cw[6], cw[7]));
 }
 
 // Reverse activation of my 8 columns of one group: v = delta_{l-1} = D * softplus'(z_{l-1}); the sign of element n is
@@ -228,7 +241,7 @@ __device__ __forceinline__ void t2_fwd_layer(const T2Epi& c, T2Bars* bars, int l
   const uint32_t dcol = c.tl + ((l & 1) ? T2_D1 : T2_D0) + c.part * 8;
   const uint32_t bar0 = tc::smem_u32(&bars->a_grp[0]);
   constexpr bool SIGNAL = !HEAD || GRAD;
-  const bool dbg_noact = (c.dbg & 8) != 0, dbg_noscratch = (c.dbg & 16) != 0;
+  const bool dbg_noact = T2_DBG(c.dbg, 8), dbg_noscratch = T2_DBG(c.dbg, 16);
   uint32_t sgn = 0;
   uint32_t da[8], db[8];
   tc::tmem_ld8(dcol, da);
@@ -286,7 +299,7 @@ __device__ __forceinline__ void t2_bwd_layer(const T2Epi& c, T2Bars* bars, int p
                                              int lane, uint8_t* smem, int& trace_n, int trace_slot) {
   const uint32_t dbase = c.tl + ((p & 1) ? T2_D1 : T2_D0) + c.part * 8;
   const uint32_t bar0 = tc::smem_u32(&bars->a_grp[0]);
-  const bool dbg_noact = (c.dbg & 8) != 0, dbg_noscratch = (c.dbg & 16) != 0;
+  const bool dbg_noact = T2_DBG(c.dbg, 8), dbg_noscratch = T2_DBG(c.dbg, 16);
   const uint4* codes = c.scratch + (size_t)(lsrc * 4) * T2_EPI_THREADS + c.te;
   uint32_t sgn = c.sgn_scratch[(size_t)lsrc * T2_EPI_THREADS + c.te];
   uint4 spa = codes[0], spb = make_uint4(0u, 0u, 0u, 0u);
@@ -512,7 +525,7 @@ k_sdf_tc2(const DevScene sc, const DevNet net, const PointSource src, const uint
   } else if (warp == T2_EPI_WARPS) {
     // =============================== the MMA issuer ===============================
     const bool fast = (flags & 2) != 0;       // single fp16 MMA per product (opt-in reduced-precision mode)
-    const bool nomma = (flags & 4) != 0;      // timing experiment: skip the tcgen05.mma instructions (results invalid)
+    const bool nomma = T2_DBG(flags, 4);      // timing experiment: skip the tcgen05.mma instructions (results invalid)
     if (tc::elect_one()) {
       const uint32_t ring = tc::smem_u32(smem + S2_RING);
       const uint32_t tAhi = tbase + T2_AHI, tAlo = tbase + T2_ALO;
@@ -686,7 +699,7 @@ k_sdf_tc2(const DevScene sc, const DevNet net, const PointSource src, const uint
 #pragma unroll
         for (int lv = 0; lv < 4; ++lv) {
           float f7[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-          if (lv < sc.n_levels && !(flags & 64)) sparse_level<0>(sc, lv, px, py, pz, nullptr, f7);
+          if (lv < sc.n_levels && !T2_DBG(flags, 64)) sparse_level<0>(sc, lv, px, py, pz, nullptr, f7);
 #pragma unroll
           for (int c = 0; c < 7; ++c) put_k(afeat, r, lv * 7 + c, f7[c]);
         }
@@ -728,7 +741,7 @@ k_sdf_tc2(const DevScene sc, const DevNet net, const PointSource src, const uint
         float acc[3] = {0.f, 0.f, 0.f};
 #pragma unroll
         for (int lv = 0; lv < 4; ++lv) {
-          if (lv < sc.n_levels && !(flags & 64)) {
+          if (lv < sc.n_levels && !T2_DBG(flags, 64)) {
             float g7[7], o3[3] = {0.f, 0.f, 0.f};
 #pragma unroll
             for (int c = 0; c < 7; ++c) g7[c] = s_gf[(lv * 7 + c) * 128 + r];
@@ -768,7 +781,7 @@ k_sdf_tc2(const DevScene sc, const DevNet net, const PointSource src, const uint
       for (int64_t s = 0; s < total; ++s, slot = (slot + 1 == T2_NSLOT) ? 0 : slot + 1, par ^= (slot == 0),
                    cid = (cid + 1 == nch_tile) ? 0 : cid + 1) {
         if (s >= T2_NSLOT) tc::mbar_wait(&bars->w_empty[slot], par);
-        if (flags & 32) {           // timing experiment: no weight traffic
+        if (T2_DBG(flags, 32)) {    // timing experiment: no weight traffic
           tc::mbar_arrive(&bars->w_full[slot]);
           continue;
         }
