@@ -606,7 +606,32 @@ def run_gpu(args):
                 "mode": "dense (parity mode, Q16)", "tflops": R ** 3 * FLOP_PER_POINT_FWD / (ms_grid * 1e-3) / 1e12,
                 "parallelism": "1 GPU" if world == 1 else "x-slabs over %d ranks + NCCL all-gather of the slabs "
                                "inside the timed region" % world}
-        del step_grid
+        # the rest of extract_geometry on the gathered grid: GPU marching cubes (replaces host PyMCubes), and the
+        # opt-in sparsified query (BASELINE configs[2] "with surface-region sparsification": points outside the 4-level
+        # voxel mask get a constant — NOT result-identical outside the mask, Q16)
+        from surf_b200 import mesh as smesh
+        u_full = step_grid()
+
+        def step_mc():
+            return smesh.marching_cubes_device(u_full, 0.0)
+        v_mc, t_mc = step_mc()
+        ms_mc = timed(step_mc, 2) / 2
+        grid["marching_cubes"] = {"ms": ms_mc, "vertices": int(v_mc.shape[0]), "triangles": int(t_mc.shape[0]),
+                                  "gb_per_s": (R ** 3 * 12.0) / (ms_mc * 1e-3) / 1e9,
+                                  "note": "GPU marching cubes of the full grid incl. the host read of the output sizes; "
+                                          "12 B / grid point algorithmic (4 B read + 4 B code word written and re-read)"}
+        del u_full, v_mc, t_mc
+
+        def step_grid_sparse():
+            u = m.sdf_grid(ps, [-1, -1, -1], [1, 1, 1], R, x_range=(x0, x1), sparsify=True)
+            if world > 1:
+                u = sdist.gather_grid(u, R)
+            return u
+        step_grid_sparse()
+        ms_sp = timed(step_grid_sparse, 2) / 2
+        grid["sparsified"] = {"value": R ** 3 / (ms_sp * 1e-3), "unit": "pts/s", "ms": ms_sp,
+                              "mode": "opt-in: SDF evaluated only inside the voxel mask (Q16)"}
+        del step_grid, step_grid_sparse
         torch.cuda.empty_cache()
 
     # ---- opt-in reduced-precision mode (north_star: 1e-2 mode), reported next to the headline, not as it ----

@@ -56,9 +56,11 @@ def compare_chunk(m, net, ps, sc_cpu, o, d, t_rand, what, expect_hit=True, min_r
     rows = explain_mask_mismatches(O, out["_point_flags"].cpu() & 1, ref["_voxel_mask"], out["mid_z_vals"],
                                    ref["mid_z_vals"], o, d, sc_cpu.mask_volumes, what + "voxel mask")
     n_mask_mism = int((~rows).sum())
-    cm_gpu = ((out["_point_flags"].cpu() >> 1) & 1).bool()
-    if n_mask_mism == 0:
-        assert_equal_int(cm_gpu, ref["_compute_mask"], what + "computed-point mask (incl. the empty-chunk fallback)")
+    # computed-point mask (= voxel mask, or the first 10 points of a chunk whose mask is empty, Q6): every ray without a
+    # proven boundary mismatch must agree sample by sample — in an empty chunk that is every ray
+    cm_gpu = ((out["_point_flags"].cpu() >> 1) & 1).bool().reshape(B, S)
+    assert_equal_int(cm_gpu[rows], ref["_compute_mask"].reshape(B, S)[rows],
+                     what + "computed-point mask (incl. the empty-chunk fallback)")
     rows = rows & explain_view_mismatches(O, out["_point_views"], ref, sc_cpu)
     g_rows, g_worst = explain_gradient_mismatches(O, out, ref, o, d, sc_cpu, net, what)
     rows = rows & g_rows
