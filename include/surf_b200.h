@@ -46,7 +46,7 @@ typedef struct surf_net surf_net;     /* opaque: folded / re-laid-out network we
  * volume.py:99-132) in RENDERER order (lists already reversed, surf.py:159):
  * volume lists fine->coarse, feature lists high-res->low-res. */
 typedef struct surf_scene_inputs {
-  int32_t n_levels;                             /* 1..4 */
+  int32_t n_levels;                             /* 1..4; 0 = matching-volume-only scene (surf_depth_map) */
   int32_t feat_ch;                              /* channels per level (7) */
   int32_t dim[SURF_MAX_LEVELS];                 /* cubic volume dim N_l */
   int64_t n_vox[SURF_MAX_LEVELS];               /* rows of volumes[l] */
@@ -265,6 +265,28 @@ int surf_render_extras(surf_scene* s, const surf_net* n, const surf_extras_param
                        const float* d_rays_d, const float* d_z_cross, const float* d_z_max, int64_t n_rays,
                        float* d_pts_sdf0, float* d_normal_sdf0, float* d_ref_val, float* d_src_val, void* d_workspace,
                        size_t workspace_bytes, int32_t mlp_mode, void* stream);
+
+/* ---- matching field -------------------------------------------------------------------------
+ * MatchingField.forward for ONE view (matching_field.py:74-141): depth map of the view at (h,w) from the scene's dense
+ * matching volume — per pixel 1 window [near, far] (stage 0) or 2 windows around the previous stage's depth (widths
+ * range * ratio[0] and range * ratio[1], :101-121), n_samples uniform depths per window (+ jitter when d_t_rand (h*w,
+ * n_windows) raw U[0,1) is given), sorted together, softmax of the trilinear probes -> expected depth * cos
+ * (depth_render, :18-72) — then F.interpolate(bilinear) to (img_h, img_w) when d_depth_full is not NULL (:136).
+ * Host-side (torch, like the reference): Kinv = intrs.inverse()[view,:3,:3], R = c2w[:3,:3], C = c2w[:3,3],
+ * Rinv2 = row 2 of inverse(c2w[:3,:3]); d_lin = linspace(0,1,n_samples), d_tx = linspace(0,img_w-1,w),
+ * d_ty = linspace(0,img_h-1,h); d_pre_depth (img_h,img_w) = previous stage's full-resolution map.
+ * d_occ_partials (h*w,3): per ray [sum of the first 6 densities, sum density * outside_sphere, sum outside_sphere]
+ * (occ_reg = col0.sum() / (6 h w) + col1.sum() / (col2.sum() + 1e-10), :68). */
+typedef struct surf_depth_map_params {
+  float Kinv[9], R[9], C[3], Rinv2[3];
+  float near, far;
+  float ratio[2];               /* range_ratios[stage], range_ratios[stage-1] */
+  int32_t n_windows, n_samples;
+  int32_t h, w, img_h, img_w;
+} surf_depth_map_params;
+int surf_depth_map(const surf_scene* s, const surf_depth_map_params* p, const float* d_lin, const float* d_tx,
+                   const float* d_ty, const float* d_pre_depth, const float* d_t_rand, float* d_depth_lowres,
+                   float* d_occ_partials, float* d_depth_full, void* stream);
 
 /* ---- marching cubes -----------------------------------------------------------------------
  * Replaces the host call `mcubes.marching_cubes(u, threshold)` of extract_geometry (implicit_surface.py:353; PyMCubes

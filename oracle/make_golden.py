@@ -175,6 +175,35 @@ def case_sdf_grid(IS, name, base, scene_seed, weight_seed, resolution):
     save(name, recipe, net, {"wild_pts": wild}, {"u": u, "wild_full": full, "wild_grad": gr, "wild_smooth": sm})
 
 
+def case_matching_field(IS, name, nv, H, W, base, scene_seed, torch_seed):
+    """MatchingField.forward (matching_field.py:74-141) of the unmodified reference: stage 0 (full range), stage 1
+    (two windows around the stage-0 depths), and a jittered stage-1 pass (RNG stream: rand([B,1]) per window)."""
+    from models.modules.matching_field import MatchingField
+    sc = synthetic.make_scene(nv, H, W, base, seed=scene_seed)
+    conf = ref_loader.DictConf({"n_samples_depths": [128, 64, 32, 16], "n_importance_depths": [128, 64, 32, 16],
+                                "up_sample_steps": [4, 4, 4, 4], "depth_res_levels": [4, 2, 2, 1]})
+    mf = MatchingField(conf)
+    near_fars = torch.stack([torch.tensor([float(sc.near), float(sc.far)])] * nv)
+    ipts = {"near_fars": near_fars, "c2ws": sc.c2ws, "intrs": sc.intrs, "imgs": sc.imgs, "src_idx": 1}
+    rr = [1.0, 0.4, 0.1, 0.01]
+    out = {}
+    with torch.no_grad():
+        d0, o0 = mf(ipts, sc.matching_volume, 0, rr, None, perturb=False)
+        d1, o1 = mf(ipts, sc.matching_volume, 1, rr, d0, perturb=False)
+        torch.manual_seed(torch_seed)
+        d1p, o1p = mf(ipts, sc.matching_volume, 1, rr, d0, perturb=True)
+        d3, o3 = mf(ipts, sc.matching_volume, 3, rr, d1, perturb=False)
+    for tag, (dd, oo) in {"s0": (d0, o0), "s1": (d1, o1), "s1p": (d1p, o1p), "s3": (d3, o3)}.items():
+        out["depth_" + tag] = torch.stack(dd)
+        out["occ_" + tag] = torch.stack(oo)
+    recipe = dict(nv=nv, H=H, W=W, base=base, scene_seed=scene_seed, torch_seed=torch_seed, scene_sha=scene_checksum(sc))
+    # no network in this case: save an empty state dict through the common writer
+    class _NoNet:
+        def state_dict(self):
+            return {}
+    save(name, recipe, _NoNet(), {"near_fars": near_fars}, out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     IS = ref_loader.load_reference()
@@ -196,6 +225,8 @@ def main():
                   torch_seed=0)
     # F: SDF grid + out-of-range points
     case_sdf_grid(IS, "sdf_grid_24", base=8, scene_seed=1, weight_seed=0, resolution=24)
+    # G: the upstream user of the probe kernel: MatchingField.forward
+    case_matching_field(IS, "matching_field", nv=3, H=48, W=64, base=8, scene_seed=1, torch_seed=9)
 
 
 if __name__ == "__main__":

@@ -684,6 +684,93 @@ def composite_envelope(ref, sdf_g, grad_g, color_g, rays_o, rays_d, inv_s, rot0_
 
 
 # ----------------------------------------------------------------------------------------------
+# MatchingField  (matching_field.py:18-141): the probe of the matching volume run for every pixel of every view
+# ----------------------------------------------------------------------------------------------
+def matching_depth_render(rays_o, rays_d, near, far, c2w, matching_volume, n_samples, t_rand=None):
+    """matching_field.py:18-72.  near / far (B, n_windows); per window n_samples uniform depths (+ jitter
+    (t_rand[:, i] - 0.5) * (far - near) / n when t_rand (B, n_windows) of raw U[0,1) draws is given), all windows
+    sorted together, softmax of the trilinear probes -> expected depth.  Returns (render_depth (B,), occ_reg scalar,
+    z_vals (B,S), density (B,S))."""
+    rays_o, rays_d = rays_o.reshape(-1, 3), rays_d.reshape(-1, 3)
+    B = rays_o.shape[0]
+    zs = []
+    for i in range(near.shape[-1]):
+        ns, fs = near[..., [i]], far[..., [i]]
+        z = ns + (fs - ns) * torch.linspace(0.0, 1.0, n_samples)[None, :]
+        if t_rand is not None:
+            z = z + (t_rand[:, i:i + 1] - 0.5) * (fs - ns) / n_samples
+        zs.append(z)
+    z_vals, _ = torch.sort(torch.cat(zs, dim=-1), dim=-1)
+    pts = (rays_o[:, None, :] + rays_d[:, None, :] * z_vals[..., :, None]).reshape(-1, 3)
+    outside = (torch.linalg.norm(pts, ord=2, dim=-1, keepdim=True).reshape(B, -1) > 1.0).float()
+    density = lookup_dense(pts, matching_volume, "bilinear").reshape(B, -1)
+    weights = F.softmax(density, dim=-1)
+    cam_d = torch.matmul(torch.inverse(c2w[None, :3, :3]), rays_d[:, :, None]).squeeze()
+    render_depth = (z_vals * weights).sum(dim=1) * cam_d[:, 2]
+    occ_reg = density[:, :6].mean() + (density * outside).sum() / (outside.sum() + 1e-10)
+    return render_depth, occ_reg, z_vals, density
+
+
+def matching_rays(intrs, c2ws, view, img_h, img_w, level):
+    """matching_field.py:79-100: the pixel grid of a depth map at 1/level resolution and its rays in view `view`."""
+    h, w = img_h // level, img_w // level
+    tx = torch.linspace(0, img_w - 1, w)
+    ty = torch.linspace(0, img_h - 1, h)
+    py, px = torch.meshgrid(ty, tx, indexing="ij")
+    px, py = px.reshape(-1), py.reshape(-1)
+    pix = torch.stack([px, py, torch.ones_like(px)], dim=-1).float()
+    cam = torch.matmul(intrs.inverse()[view, None, :3, :3], pix[:, :, None]).squeeze()
+    d = cam / torch.linalg.norm(cam, ord=2, dim=-1, keepdim=True)
+    d = torch.matmul(c2ws[view, None, :3, :3], d[:, :, None]).squeeze()
+    o = c2ws[view, None, :3, 3].expand(d.shape)
+    return o, d, px, py, h, w
+
+
+def matching_windows(near_ori, far_ori, pre_z, ratio):
+    """matching_field.py:107-121: a window of width (far - near) * ratio around pre_z, shifted into [near, far]."""
+    sr = (far_ori - near_ori).squeeze() * ratio
+    near = (pre_z - sr / 2).unsqueeze(1)
+    far = (pre_z + sr / 2).unsqueeze(1)
+    near = torch.where(far > far_ori, near - (far - far_ori), near)
+    far = torch.where(near < near_ori, far + (near_ori - near), far)
+    near = torch.clamp(near, near_ori.squeeze(), far_ori.squeeze())
+    far = torch.clamp(far, near_ori.squeeze(), far_ori.squeeze())
+    return near, far
+
+
+def matching_field_forward(n_samples_depths, depth_res_levels, ipts, matching_volume, stage_idx, range_ratios,
+                           pre_depths=None, perturb=False):
+    """MatchingField.forward (matching_field.py:74-141): a depth map per view at the stage's resolution, bilinearly
+    up-sampled to the image size, + the occupancy regulariser per view."""
+    near_fars, c2ws, intrs = ipts["near_fars"], ipts["c2ws"], ipts["intrs"]
+    src_idx = ipts["src_idx"] if "src_idx" in ipts else 0
+    img_h, img_w = ipts["imgs"].shape[-2:]
+    level = depth_res_levels[stage_idx]
+    n = n_samples_depths[stage_idx]
+    depths, occs = [], []
+    for i in range(intrs.shape[0]):
+        o, d, px, py, h, w = matching_rays(intrs, c2ws, i, img_h, img_w, level)
+        near_ori, far_ori = near_fars[i].reshape(1, 2).split(split_size=1, dim=1)
+        if pre_depths is not None:
+            pre = pre_depths[i].detach()[(py.long(), px.long())]
+            cam_d = torch.matmul(torch.inverse(c2ws[i, None, :3, :3]), d[:, :, None]).squeeze()
+            pre_z = pre.reshape(-1) / cam_d[:, 2]
+            n1, f1 = matching_windows(near_ori, far_ori, pre_z, range_ratios[stage_idx])
+            n0, f0 = matching_windows(near_ori, far_ori, pre_z, range_ratios[stage_idx - 1])
+            near, far = torch.cat([n1, n0], dim=1), torch.cat([f1, f0], dim=1)
+        else:
+            near, far = near_ori.repeat(o.shape[0], 1), far_ori.repeat(o.shape[0], 1)
+        t_rand = None
+        if perturb and (i == 0 or i == src_idx):
+            t_rand = torch.cat([torch.rand([o.shape[0], 1]) for _ in range(near.shape[-1])], dim=1)
+        rd, occ, _, _ = matching_depth_render(o, d, near, far, c2ws[i], matching_volume, n, t_rand)
+        rd = F.interpolate(rd.reshape(1, 1, h, w), size=(img_h, img_w), mode="bilinear").squeeze(0).squeeze(0)
+        depths.append(rd)
+        occs.append(occ)
+    return depths, occs
+
+
+# ----------------------------------------------------------------------------------------------
 # training extras  (implicit_surface.py:172, 218-245; projector.py:560-645)
 # ----------------------------------------------------------------------------------------------
 def sdf_gradient_smooth(net: OracleNet, pts: torch.Tensor, volumes, indexes):

@@ -35,7 +35,7 @@ EXPORTS = [
     "surf_point_mask", "surf_lookup_sparse", "surf_lookup_feature", "surf_blend", "surf_point_flags",
     "surf_tc_selftest",
     "surf_mc_workspace_bytes", "surf_mc_count", "surf_mc_emit",
-    "surf_extras_workspace_bytes", "surf_render_extras",
+    "surf_extras_workspace_bytes", "surf_render_extras", "surf_depth_map",
 ]
 
 
@@ -133,6 +133,13 @@ class ExtrasParams(C.Structure):
                 ("RC", (C.c_float * 3) * MAX_VIEWS), ("n_src", C.c_int32), ("patch_size", C.c_int32)]
 
 
+class DepthMapParams(C.Structure):
+    """surf_depth_map_params (include/surf_b200.h)."""
+    _fields_ = [("Kinv", C.c_float * 9), ("R", C.c_float * 9), ("C", C.c_float * 3), ("Rinv2", C.c_float * 3),
+                ("near", C.c_float), ("far", C.c_float), ("ratio", C.c_float * 2), ("n_windows", C.c_int32),
+                ("n_samples", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("img_h", C.c_int32), ("img_w", C.c_int32)]
+
+
 class RenderOutputs(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in RENDER_OUTPUT_FIELDS]
 
@@ -199,6 +206,8 @@ def _declare(lib):
     lib.surf_extras_workspace_bytes.argtypes = [i64]
     lib.surf_render_extras.restype = C.c_int
     lib.surf_render_extras.argtypes = [vp, vp, P(ExtrasParams), vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, C.c_size_t, i32, vp]
+    lib.surf_depth_map.restype = C.c_int
+    lib.surf_depth_map.argtypes = [vp, P(DepthMapParams), vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.surf_mc_workspace_bytes.restype = C.c_size_t
     lib.surf_mc_workspace_bytes.argtypes = [i32, i32, i32]
     lib.surf_mc_count.restype = C.c_int

@@ -14,17 +14,6 @@
 //                      = H (u, v, 1) / (w + 1e-8), grid_sample(bilinear, zeros, align_corners=True).
 #include "surf_internal.cuh"
 
-// F.interpolate(mode="bilinear", align_corners=False) source index / weight (ATen area_pixel_compute_source_index)
-__device__ __forceinline__ void up_src(int dst, float scale, int in_size, int* i0, int* i1, float* l1) {
-  float src = __fsub_rn(__fmul_rn(scale, __fadd_rn((float)dst, 0.5f)), 0.5f);
-  if (src < 0.f) src = 0.f;
-  int a = (int)src;
-  if (a > in_size - 1) a = in_size - 1;
-  *i0 = a;
-  *i1 = a + ((a < in_size - 1) ? 1 : 0);
-  *l1 = __fsub_rn(src, (float)a);
-}
-
 __device__ __forceinline__ float4 up_tap(const float4* __restrict__ f, int w, int y0, int y1, int x0, int x1, float ly,
                                          float lx) {
   const float4 a = __ldg(f + (size_t)y0 * w + x0), b = __ldg(f + (size_t)y0 * w + x1);

@@ -286,7 +286,8 @@ extern "C" int surf_scene_set_views(surf_scene* s, const surf_scene_views* in, v
 
 extern "C" int surf_scene_create(const surf_scene_inputs* in, void* stream, surf_scene** out) {
   SURF_CHECK_ARG(in && out, "inputs/out null");
-  SURF_CHECK_ARG(in->n_levels >= 1 && in->n_levels <= SURF_MAX_LEVELS, "n_levels must be 1..4");
+  SURF_CHECK_ARG(in->n_levels >= 0 && in->n_levels <= SURF_MAX_LEVELS, "n_levels must be 0..4");
+  SURF_CHECK_ARG(in->n_levels >= 1 || in->d_matching_volume != nullptr, "a scene without volume levels needs a matching volume");
   SURF_CHECK_ARG(in->feat_ch >= 1 && in->feat_ch <= 7, "feat_ch must be 1..7");
   SURF_CHECK_ARG(in->n_views >= 0 && in->n_views - 1 <= SURF_MAX_VIEWS, "n_views out of range");
   cudaStream_t st = (cudaStream_t)stream;

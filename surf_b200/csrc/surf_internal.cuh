@@ -268,6 +268,17 @@ __device__ __forceinline__ void sparse_prefetch_l2(const DevScene& sc, int l, fl
   }
 }
 
+// F.interpolate(mode="bilinear", align_corners=False) source index / weight (ATen area_pixel_compute_source_index)
+__device__ __forceinline__ void up_src(int dst, float scale, int in_size, int* i0, int* i1, float* l1) {
+  float src = __fsub_rn(__fmul_rn(scale, __fadd_rn((float)dst, 0.5f)), 0.5f);
+  if (src < 0.f) src = 0.f;
+  int a = (int)src;
+  if (a > in_size - 1) a = in_size - 1;
+  *i0 = a;
+  *i1 = a + ((a < in_size - 1) ? 1 : 0);
+  *l1 = __fsub_rn(src, (float)a);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -60,17 +60,20 @@ class PreparedScene:
             volumes, sparse_idxes = [volumes], [sparse_idxes]
             if mask_volumes is not None and isinstance(mask_volumes, torch.Tensor):
                 mask_volumes = [mask_volumes]
-        dev = volumes[0].device
+        volumes, sparse_idxes = list(volumes), list(sparse_idxes)
+        n_levels = len(volumes)
+        if n_levels == 0 and matching_volume is None:
+            raise ValueError("a scene needs volume levels or a matching volume")
+        dev = volumes[0].device if n_levels else matching_volume.device
         if dev.type != "cuda":
             raise RuntimeError("surf_b200: scene tensors must live on a CUDA device (no CPU fallback)")
         self.device = dev
-        n_levels = len(volumes)
-        if not (1 <= n_levels <= _lib.MAX_LEVELS):
-            raise ValueError("1..4 volume levels supported")
+        if n_levels > _lib.MAX_LEVELS:
+            raise ValueError("at most 4 volume levels supported")
         keep = []
         inp = _lib.SceneInputs()
         inp.n_levels = n_levels
-        inp.feat_ch = int(volumes[0].shape[1])
+        inp.feat_ch = int(volumes[0].shape[1]) if n_levels else 7      # 0 levels: matching-volume-only (MatchingField)
         for l in range(n_levels):
             v = _f32c(volumes[l])
             idx = sparse_idxes[l].detach()

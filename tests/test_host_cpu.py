@@ -89,6 +89,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_sizes_match_header():
     # mirrors of the POD structs: a size drift means the ctypes binding no longer matches the header
     assert ctypes.sizeof(_lib.RenderOutputs) == 22 * 8
+    assert ctypes.sizeof(_lib.DepthMapParams) == 4 * (9 + 9 + 3 + 3 + 2 + 2 + 6)
     assert ctypes.sizeof(_lib.ExtrasParams) == 4 * (9 + 3 + 9 + 9 + 8 * 9 + 8 * 9 + 8 * 3 + 2)
     assert ctypes.sizeof(_lib.RenderCfg) == 4 + 16 + 16 + 4 + 4 + 4 + 4 + 4 + 8 + 8  # incl. alignment padding
     assert ctypes.sizeof(_lib.SceneStats) == 9 * 8

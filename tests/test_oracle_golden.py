@@ -134,3 +134,20 @@ def test_training_extras_match_the_reference(name):
         assert out[k].shape == tuple(g["out"][k].shape)
         assert_close(out[k], g["out"][k], 1e-6, k)
     assert_close(out["smooth_error"], g["out"]["smooth_error"], 1e-5, "smooth_error")
+
+
+def test_matching_field_matches_the_reference():
+    """MatchingField.forward (matching_field.py:74-141) restated in the oracle vs the unmodified reference: stage 0,
+    stage 1 (two windows around the stage-0 depth), a jittered pass, stage 3 at full resolution."""
+    g = load_golden("matching_field")
+    sc = scene_from_recipe(g["recipe"])
+    ipts = {"near_fars": g["in"]["near_fars"], "c2ws": sc.c2ws, "intrs": sc.intrs, "imgs": sc.imgs, "src_idx": 1}
+    rr, ns, lv = [1.0, 0.4, 0.1, 0.01], [128, 64, 32, 16], [4, 2, 2, 1]
+    d0, o0 = O.matching_field_forward(ns, lv, ipts, sc.matching_volume, 0, rr, None)
+    d1, o1 = O.matching_field_forward(ns, lv, ipts, sc.matching_volume, 1, rr, d0)
+    torch.manual_seed(int(g["recipe"]["torch_seed"]))
+    d1p, o1p = O.matching_field_forward(ns, lv, ipts, sc.matching_volume, 1, rr, d0, perturb=True)
+    d3, o3 = O.matching_field_forward(ns, lv, ipts, sc.matching_volume, 3, rr, d1)
+    for tag, (dd, oo) in {"s0": (d0, o0), "s1": (d1, o1), "s1p": (d1p, o1p), "s3": (d3, o3)}.items():
+        assert_close(torch.stack(dd), g["out"]["depth_" + tag], 1e-6, "depth " + tag)
+        assert_close(torch.stack(oo), g["out"]["occ_" + tag], 1e-6, "occ_reg " + tag)
