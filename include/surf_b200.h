@@ -266,6 +266,46 @@ int surf_render_extras(surf_scene* s, const surf_net* n, const surf_extras_param
                        float* d_pts_sdf0, float* d_normal_sdf0, float* d_ref_val, float* d_src_val, void* d_workspace,
                        size_t workspace_bytes, int32_t mlp_mode, void* stream);
 
+/* ---- volume producers ----------------------------------------------------------------------
+ * models/modules/volume.py:54-168 — the functions that build the scene tensors.  Cameras are HOST matrices formed
+ * like the reference (h_w2cs = inverse(c2ws), h_intrs = the 4x4 intrinsics, (nv,4,4) row-major).
+ *   surf_volume_back_proj    Volume.back_proj_multiscale (:54-97): d_feats[s] = the feature scales that are summed
+ *                            (feats[stage_idx:], NCHW (nv,4,h_s,w_s)); norm_h/norm_w = size of the finest map (the
+ *                            projection is normalised with it); h_agg_mlp = [0.weight (8,4), 0.bias (8), 2.weight (1,8),
+ *                            2.bias (1)] of Volume.agg_mlp.  -> d_feat_vol (n,8) = [mean4 | var4], d_mask_vol (n) 0/1.
+ *   surf_volume_depth_filter Volume.depth_filtering (:134-168): d_depths (nv,h,w), norm_h/w = (h,w); -> d_valid (n) 0/1.
+ *   surf_volume_upsample2x   F.interpolate(scale_factor=2, "trilinear") of a (D,H,W) volume (sparse2dense, :108).
+ *   surf_scene_create_sparse sparse2dense + get_index (:99-132) for all levels, emitting the prepared layout of the
+ *                            render path directly (int32 index, 1-bit masks, 8-float voxel rows, fp32 matching volume
+ *                            = finest logits scattered over the 2x up-sampled coarser volumes).  Levels in BUILD order
+ *                            (coarse -> fine, dims doubling); d_coords[b] (n_b,3) fp32 integer voxel coordinates,
+ *                            row i of d_volumes[b] (n_b,feat_ch) belongs to coordinate i; d_logits[b] (n_b) nullable
+ *                            (no sampler).  The result is a regular scene handle; views are installed with surf_scene_set_views. */
+typedef struct surf_volume_views {
+  int32_t n_views;
+  int32_t norm_h, norm_w;
+  const float* h_w2cs;                          /* HOST (nv,4,4) = inverse(c2ws) */
+  const float* h_intrs;                         /* HOST (nv,4,4) */
+} surf_volume_views;
+typedef struct surf_scene_sparse_inputs {
+  int32_t n_levels;
+  int32_t feat_ch;
+  int32_t dim[SURF_MAX_LEVELS];
+  int64_t n_vox[SURF_MAX_LEVELS];
+  const float* d_coords[SURF_MAX_LEVELS];
+  const float* d_volumes[SURF_MAX_LEVELS];
+  const float* d_logits[SURF_MAX_LEVELS];
+} surf_scene_sparse_inputs;
+int surf_volume_back_proj(const surf_volume_views* vw, const float* const* d_feats, const int32_t* feat_h,
+                          const int32_t* feat_w, int32_t n_scales, int32_t n_channels, const float* h_agg_mlp,
+                          const float* d_coords, int64_t n_vox, const float* voxel_size, const float* origin,
+                          float* d_feat_vol, uint8_t* d_mask_vol, void* stream);
+int surf_volume_depth_filter(const surf_volume_views* vw, const float* d_depths, const float* d_coords, int64_t n_vox,
+                             const float* voxel_size, const float* origin, float depth_range, uint8_t* d_valid,
+                             void* stream);
+int surf_volume_upsample2x(const float* d_in, int32_t D, int32_t H, int32_t W, float* d_out, void* stream);
+int surf_scene_create_sparse(const surf_scene_sparse_inputs* in, void* stream, surf_scene** out);
+
 /* ---- matching field -------------------------------------------------------------------------
  * MatchingField.forward for ONE view (matching_field.py:74-141): depth map of the view at (h,w) from the scene's dense
  * matching volume — per pixel 1 window [near, far] (stage 0) or 2 windows around the previous stage's depth (widths

@@ -204,6 +204,43 @@ def case_matching_field(IS, name, nv, H, W, base, scene_seed, torch_seed):
     save(name, recipe, _NoNet(), {"near_fars": near_fars}, out)
 
 
+def case_volume(IS, name, nv, H, W, base, scene_seed, weight_seed):
+    """The producers of the scene tensors (volume.py:21-168) of the unmodified reference on synthetic inputs: two
+    stages of init_coords / back_proj_multiscale / sparse2dense / get_index / up_sample / depth_filtering."""
+    from models.modules.volume import Volume
+    sc = synthetic.make_scene(nv, H, W, base, seed=scene_seed)
+    torch.manual_seed(weight_seed)
+    vol = Volume(ref_loader.DictConf({"base_volume_dim": [base, base, base]}))
+    feats = [f for f in sc.features[::-1]]            # coarse -> fine, as feature_network emits them
+    g = torch.Generator().manual_seed(weight_seed + 1)
+    out = {}
+    with torch.no_grad():
+        c0 = vol.init_coords().type_as(sc.intrs)
+        fv0, m0 = vol.back_proj_multiscale(feats, c0, sc.intrs, sc.c2ws, 0)
+        c0m, fv0m = c0[m0], fv0[m0]
+        reg0 = torch.randn(c0m.shape[0], 8, generator=g)                      # stand-in for reg_network's output
+        mv0, mk0 = vol.sparse2dense(reg0[:, :1], c0m, None)
+        idx0 = vol.get_index(c0m)
+        depths = [torch.full((H, W), 2.0) + 0.05 * torch.randn(H, W, generator=g) for _ in range(nv)]
+        c1, f1 = vol.up_sample(c0m.clone(), reg0)
+        keep = None
+        c1f, f1f = vol.depth_filtering(depths, c1, f1, sc.intrs, sc.c2ws, 0.4)
+        fv1, m1 = vol.back_proj_multiscale(feats, c1f, sc.intrs, sc.c2ws, 1)
+        c1m = c1f[m1]
+        reg1 = torch.randn(c1m.shape[0], 8, generator=g)
+        mv1, mk1 = vol.sparse2dense(reg1[:, :1], c1m, mv0)
+        idx1 = vol.get_index(c1m)
+    out.update({"c0": c0, "fv0": fv0, "m0": m0, "reg0": reg0, "mv0": mv0, "mk0": mk0, "idx0": idx0,
+                "depths": torch.stack(depths), "c1": c1, "f1": f1, "c1f": c1f, "f1f": f1f, "fv1": fv1, "m1": m1,
+                "reg1": reg1, "mv1": mv1, "mk1": mk1, "idx1": idx1})
+    recipe = dict(nv=nv, H=H, W=W, base=base, scene_seed=scene_seed, weight_seed=weight_seed, scene_sha=scene_checksum(sc))
+
+    class _Agg:
+        def state_dict(self_inner):
+            return {"agg_mlp." + k: v for k, v in vol.agg_mlp.state_dict().items()}
+    save(name, recipe, _Agg(), {}, out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     IS = ref_loader.load_reference()
@@ -227,6 +264,8 @@ def main():
     case_sdf_grid(IS, "sdf_grid_24", base=8, scene_seed=1, weight_seed=0, resolution=24)
     # G: the upstream user of the probe kernel: MatchingField.forward
     case_matching_field(IS, "matching_field", nv=3, H=48, W=64, base=8, scene_seed=1, torch_seed=9)
+    # H: the producers of the scene tensors: Volume.*
+    case_volume(IS, "volume", nv=3, H=48, W=64, base=8, scene_seed=1, weight_seed=4)
 
 
 if __name__ == "__main__":

@@ -771,6 +771,98 @@ def matching_field_forward(n_samples_depths, depth_res_levels, ipts, matching_vo
 
 
 # ----------------------------------------------------------------------------------------------
+# Volume  (volume.py:21-168): producers of the scene tensors
+# ----------------------------------------------------------------------------------------------
+def volume_voxel_size(dims, bounding=((-1.0, 1.0), (-1.0, 1.0), (-1.0, 1.0))):
+    """volume.py:22-23: float64 numpy voxel size and origin of a (dx,dy,dz) grid spanning the bounding box."""
+    import numpy as np
+    b = np.array(bounding, dtype=np.float64)
+    return (b[:, 1] - b[:, 0]) / (np.array(dims) - 1), b[:, 0]
+
+
+def volume_init_coords(dims):
+    """volume.py:21-33: integer grid coordinates (n,3) fp32, x-major."""
+    g = torch.stack(torch.meshgrid(*[torch.arange(0, int(d)) for d in dims], indexing="ij")).float()
+    return g.view(3, -1).permute(1, 0).contiguous()
+
+
+def volume_up_sample(pre_coords, pre_feat, num=8):
+    """volume.py:35-52: every voxel -> its 8 children at twice the resolution (coords * 2 + offset), features repeated.
+    (The reference doubles ``pre_coords`` in place; this restatement does not mutate its input.)"""
+    c2 = pre_coords * 2
+    offs = torch.tensor([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1], [1, 1, 0], [1, 0, 1], [0, 1, 1], [1, 1, 1]],
+                        dtype=c2.dtype)[:num]
+    up_coords = (c2[:, None, :] + offs[None, :, :]).reshape(-1, 3)
+    up_feat = pre_feat[:, None, :].expand(-1, num, -1).reshape(-1, pre_feat.shape[1])
+    return up_coords, up_feat
+
+
+def _volume_project(coords, voxel_size, origin, intrs, c2ws, h, w):
+    world = coords * torch.tensor(voxel_size).type_as(coords)[None] + torch.tensor(origin).type_as(coords)[None]
+    world = world[None].permute(0, 2, 1).contiguous()
+    world = torch.cat([world, torch.ones_like(world[:, :1])], dim=1)                  # (1,4,n)
+    cam = torch.matmul(torch.inverse(c2ws), world)
+    img = torch.matmul(intrs, cam)[:, :3]
+    xy = img[:, :2] / img[:, 2:]
+    nx = xy[:, 0] / ((w - 1) / 2) - 1
+    ny = xy[:, 1] / ((h - 1) / 2) - 1
+    mask = (nx.abs() <= 1) & (ny.abs() <= 1) & (img[:, 2] > 0)                        # (nv,n)
+    return torch.stack([nx, ny], dim=-1), mask, img[:, 2:]
+
+
+def volume_back_proj(agg, feats, coords, voxel_size, origin, intrs, c2ws, stage_idx):
+    """volume.py:54-97.  feats: coarse->fine list of (nv,c,h,w); agg = dict of agg_mlp weights ('0.weight', '0.bias',
+    '2.weight', '2.bias').  Projects every voxel into every view, sums the bilinear samples of the feature scales
+    stage_idx.., scores each view with the 4->8->1 MLP, masked softmax over the views -> (mean | 'variance') (n,2c),
+    and the >= 2-view frustum mask."""
+    nv, c, h, w = feats[-1].shape
+    grid, mask, _ = _volume_project(coords, voxel_size, origin, intrs, c2ws, h, w)
+    warp = 0
+    for f in feats[stage_idx:]:
+        warp = warp + F.grid_sample(f, grid.unsqueeze(1), padding_mode="zeros", align_corners=True).reshape(nv, c, -1)
+    warp = warp.permute(0, 2, 1).contiguous()                                          # (nv,n,c)
+    x = F.linear(F.elu(F.linear(warp, agg["0.weight"], agg["0.bias"])), agg["2.weight"], agg["2.bias"])
+    x = x.masked_fill(mask.unsqueeze(-1) == 0, -1e9)
+    wv = F.softmax(x, dim=0)
+    mean = (warp * wv).sum(dim=0)
+    var = ((warp * wv) ** 2).sum(dim=0) - (warp * wv).sum(dim=0) ** 2
+    return torch.cat([mean, var], dim=1), mask.sum(dim=0) > 1
+
+
+def volume_depth_filter_mask(depths, coords, voxel_size, origin, intrs, c2ws, depth_range):
+    """volume.py:134-168: a voxel survives when its depth agrees (within depth_range) with the rendered depth map in at
+    least two views.  depths: list of (h,w).  Returns the bool (n,) mask."""
+    d = torch.stack(depths, dim=0).unsqueeze(1)
+    nv, _, h, w = d.shape
+    grid, mask, cz = _volume_project(coords, voxel_size, origin, intrs, c2ws, h, w)
+    wd = F.grid_sample(d, grid.unsqueeze(1), padding_mode="zeros", align_corners=True).reshape(nv, 1, -1)
+    valid = ((wd - cz).abs() < depth_range) & mask.unsqueeze(1)
+    return (valid.sum(0) > 1).squeeze(0)
+
+
+def volume_sparse2dense(feats, coords, dims, pre_volume=None):
+    """volume.py:99-121: scatter (n,c) voxel values into a dense (1,c,D,H,W) volume; channel 0 of the empty voxels is
+    the trilinearly 2x up-sampled previous volume.  Also the fp32 0/1 mask volume."""
+    c = feats.shape[1]
+    dense = torch.zeros([1, int(dims[0]), int(dims[1]), int(dims[2]), c])
+    if pre_volume is not None:
+        dense[..., :1] = F.interpolate(pre_volume, scale_factor=2, mode="trilinear").permute(0, 2, 3, 4, 1)
+    maskv = torch.zeros([1, int(dims[0]), int(dims[1]), int(dims[2]), 1])
+    loc = coords.to(torch.int64)
+    dense[:, loc[:, 0], loc[:, 1], loc[:, 2]] = feats
+    maskv[:, loc[:, 0], loc[:, 1], loc[:, 2]] = 1.0
+    return dense.permute(0, 4, 1, 2, 3), maskv.permute(0, 4, 1, 2, 3)
+
+
+def volume_get_index(coords, dims):
+    """volume.py:123-132: int64 table, -1 = empty, entry = row of the voxel."""
+    t = torch.full([int(dims[0]), int(dims[1]), int(dims[2])], -1, dtype=torch.int64)
+    loc = coords.to(torch.int64)
+    t[loc[:, 0], loc[:, 1], loc[:, 2]] = torch.arange(coords.shape[0], dtype=torch.int64)
+    return t
+
+
+# ----------------------------------------------------------------------------------------------
 # training extras  (implicit_surface.py:172, 218-245; projector.py:560-645)
 # ----------------------------------------------------------------------------------------------
 def sdf_gradient_smooth(net: OracleNet, pts: torch.Tensor, volumes, indexes):

@@ -36,6 +36,7 @@ EXPORTS = [
     "surf_tc_selftest",
     "surf_mc_workspace_bytes", "surf_mc_count", "surf_mc_emit",
     "surf_extras_workspace_bytes", "surf_render_extras", "surf_depth_map",
+    "surf_volume_back_proj", "surf_volume_depth_filter", "surf_volume_upsample2x", "surf_scene_create_sparse",
 ]
 
 
@@ -133,6 +134,19 @@ class ExtrasParams(C.Structure):
                 ("RC", (C.c_float * 3) * MAX_VIEWS), ("n_src", C.c_int32), ("patch_size", C.c_int32)]
 
 
+class VolumeViews(C.Structure):
+    """surf_volume_views (include/surf_b200.h)."""
+    _fields_ = [("n_views", C.c_int32), ("norm_h", C.c_int32), ("norm_w", C.c_int32), ("h_w2cs", C.c_void_p),
+                ("h_intrs", C.c_void_p)]
+
+
+class SceneSparseInputs(C.Structure):
+    """surf_scene_sparse_inputs (include/surf_b200.h)."""
+    _fields_ = [("n_levels", C.c_int32), ("feat_ch", C.c_int32), ("dim", C.c_int32 * MAX_LEVELS),
+                ("n_vox", C.c_int64 * MAX_LEVELS), ("d_coords", C.c_void_p * MAX_LEVELS),
+                ("d_volumes", C.c_void_p * MAX_LEVELS), ("d_logits", C.c_void_p * MAX_LEVELS)]
+
+
 class DepthMapParams(C.Structure):
     """surf_depth_map_params (include/surf_b200.h)."""
     _fields_ = [("Kinv", C.c_float * 9), ("R", C.c_float * 9), ("C", C.c_float * 3), ("Rinv2", C.c_float * 3),
@@ -206,6 +220,14 @@ def _declare(lib):
     lib.surf_extras_workspace_bytes.argtypes = [i64]
     lib.surf_render_extras.restype = C.c_int
     lib.surf_render_extras.argtypes = [vp, vp, P(ExtrasParams), vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, C.c_size_t, i32, vp]
+    lib.surf_volume_back_proj.restype = C.c_int
+    lib.surf_volume_back_proj.argtypes = [P(VolumeViews), P(vp), P(i32), P(i32), i32, i32, vp, vp, i64, vp, vp, vp, vp, vp]
+    lib.surf_volume_depth_filter.restype = C.c_int
+    lib.surf_volume_depth_filter.argtypes = [P(VolumeViews), vp, vp, i64, vp, vp, f32, vp, vp]
+    lib.surf_volume_upsample2x.restype = C.c_int
+    lib.surf_volume_upsample2x.argtypes = [vp, i32, i32, i32, vp, vp]
+    lib.surf_scene_create_sparse.restype = C.c_int
+    lib.surf_scene_create_sparse.argtypes = [P(SceneSparseInputs), vp, P(vp)]
     lib.surf_depth_map.restype = C.c_int
     lib.surf_depth_map.argtypes = [vp, P(DepthMapParams), vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.surf_mc_workspace_bytes.restype = C.c_size_t

@@ -218,6 +218,17 @@ static int pad_volume(surf_scene* s, int l, const float* d_volume, int64_t nvox,
   return 0;
 }
 
+// for volume.cu (surf_scene_create_sparse)
+int scene_alloc_pub(surf_scene* s, void** p, size_t bytes) { return scene_alloc(s, p, bytes); }
+int scene_pad_volume_pub(surf_scene* s, int level, const float* d_volume, int64_t n_vox, cudaStream_t st) {
+  void* p = nullptr;
+  int rc = scene_alloc(s, &p, (size_t)n_vox * 32);
+  if (rc) return rc;
+  s->dev.vol8[level] = (const float4*)p;
+  s->stats.bytes_volumes += (size_t)n_vox * 32;
+  return pad_volume(s, level, d_volume, n_vox, st);
+}
+
 extern "C" int surf_scene_update_volume(surf_scene* s, int32_t level, const float* d_volume, int64_t n_vox,
                                         void* stream) {
   SURF_CHECK_ARG(s && d_volume, "scene/volume null");

@@ -120,6 +120,49 @@ class PreparedScene:
         elif imgs is not None:
             raise ValueError("imgs given without camera matrices")
 
+    @classmethod
+    def from_sparse(cls, coords_all, volumes_all, logits_all, dims_all):
+        """Levels in BUILD order (coarse -> fine, dims doubling): coordinates (n,3), feature rows (n,feat_ch), matching
+        logits (n,) / (n,1) or None.  Emits the prepared layout directly (surf_scene_create_sparse)."""
+        lib = _lib.load()
+        self = cls.__new__(cls)
+        self._h = None
+        self._lib = lib
+        L = len(coords_all)
+        dev = coords_all[0].device
+        if dev.type != "cuda":
+            raise RuntimeError("surf_b200: scene tensors must live on a CUDA device (no CPU fallback)")
+        self.device = dev
+        inp = _lib.SceneSparseInputs()
+        inp.n_levels = L
+        inp.feat_ch = int(volumes_all[0].shape[1])
+        keep = []
+        for b in range(L):
+            co, vo = _f32c(coords_all[b]), _f32c(volumes_all[b])
+            keep += [co, vo]
+            inp.dim[b] = int(dims_all[b])
+            inp.n_vox[b] = int(co.shape[0])
+            inp.d_coords[b] = co.data_ptr()
+            inp.d_volumes[b] = vo.data_ptr() if vo.numel() else None
+            if logits_all is not None and logits_all[b] is not None:
+                lg = _f32c(logits_all[b]).reshape(-1)
+                keep.append(lg)
+                inp.d_logits[b] = lg.data_ptr()
+        self.n_levels = L
+        self.n_views = 0
+        self.n_src_views = 0
+        self.has_matching = logits_all is not None and logits_all[-1] is not None
+        self.has_images = False
+        self.intrs_host = self.c2ws_host = None
+        self._view_key = None
+        self._vol_versions = [v._version for v in volumes_all]
+        handle = C.c_void_p()
+        with torch.cuda.device(dev):
+            _lib.check(lib.surf_scene_create_sparse(C.byref(inp), _stream(), C.byref(handle)), "scene_create_sparse")
+            torch.cuda.current_stream().synchronize()
+        self._h = handle
+        return self
+
     @property
     def handle(self):
         if self._h is None:

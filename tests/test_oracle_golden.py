@@ -151,3 +151,32 @@ def test_matching_field_matches_the_reference():
     for tag, (dd, oo) in {"s0": (d0, o0), "s1": (d1, o1), "s1p": (d1p, o1p), "s3": (d3, o3)}.items():
         assert_close(torch.stack(dd), g["out"]["depth_" + tag], 1e-6, "depth " + tag)
         assert_close(torch.stack(oo), g["out"]["occ_" + tag], 1e-6, "occ_reg " + tag)
+
+
+def test_volume_producers_match_the_reference():
+    """Volume.* (volume.py:21-168) restated in the oracle vs the unmodified reference."""
+    g = load_golden("volume")
+    sc = scene_from_recipe(g["recipe"])
+    o = {k: torch.as_tensor(v) for k, v in g["out"].items()}
+    agg = {k[len("agg_mlp."):]: torch.as_tensor(v) for k, v in g["sd"].items()}
+    feats = sc.features[::-1]
+    base = int(g["recipe"]["base"])
+    vs0, org = O.volume_voxel_size([base] * 3)
+    vs1, _ = O.volume_voxel_size([2 * base] * 3)
+    c0 = O.volume_init_coords([base] * 3)
+    assert torch.equal(c0, o["c0"])
+    fv0, m0 = O.volume_back_proj(agg, feats, c0, vs0, org, sc.intrs, sc.c2ws, 0)
+    assert torch.equal(m0, o["m0"]) and torch.equal(fv0, o["fv0"])
+    c0m = c0[m0]
+    mv0, mk0 = O.volume_sparse2dense(o["reg0"][:, :1], c0m, [base] * 3)
+    assert torch.equal(mv0, o["mv0"]) and torch.equal(mk0, o["mk0"])
+    assert torch.equal(O.volume_get_index(c0m, [base] * 3), o["idx0"])
+    c1, f1 = O.volume_up_sample(c0m, o["reg0"])
+    assert torch.equal(c1, o["c1"]) and torch.equal(f1, o["f1"])
+    dm = O.volume_depth_filter_mask(list(o["depths"]), c1, vs1, org, sc.intrs, sc.c2ws, 0.4)
+    assert torch.equal(c1[dm], o["c1f"])
+    fv1, m1 = O.volume_back_proj(agg, feats, c1[dm], vs1, org, sc.intrs, sc.c2ws, 1)
+    assert torch.equal(m1, o["m1"]) and torch.equal(fv1, o["fv1"])
+    mv1, mk1 = O.volume_sparse2dense(o["reg1"][:, :1], c1[dm][m1], [2 * base] * 3, mv0)
+    assert torch.equal(mv1, o["mv1"]) and torch.equal(mk1, o["mk1"])
+    assert torch.equal(O.volume_get_index(c1[dm][m1], [2 * base] * 3), o["idx1"])
