@@ -465,6 +465,433 @@ k_blend_tc(const uint8_t* __restrict__ wtc, const float* __restrict__ wf32, floa
   if (warp == 0) tc::tmem_dealloc<64>(tbase);
 }
 
+// =============================================================================================
+// k_blend_tm: the same network with THREE tiles in flight per CTA and no block-wide barrier (round 2).
+//
+// k_blend_tc above is block-synchronous: every layer is "publish (fence + __syncthreads) -> one thread issues -> all
+// wait for the MMAs -> epilogue", ~16 block barriers and 6 exposed MMA round trips per tile with only two tiles per SM
+// (ncu r02: tensor pipe 10.6 %, issue slots 47.7 %, 1.6 barrier + 1.8 scoreboard stalls per issue).  Here
+//   * activations never touch shared memory: the epilogue writes the next A operand (fp16 hi | lo) into TMEM with
+//     tcgen05.st and the MMAs take A from TMEM (TS form), like the SDF kernel; the 32-channel residual stream x lives
+//     in registers (16 columns per thread);
+//   * a CTA runs three independent tile groups of 8 warps (warp (q, half): TMEM lane quarter q, column half) + one
+//     issuer warp; each group owns 128 TMEM columns (A hi 32 | A lo 32 | D 64) and two mbarriers (a_ready: 8 warp
+//     arrivals, d_full: tcgen05.commit), so one group's MMA round trip is hidden behind the other groups' epilogues;
+//   * the only thread synchronisation left is between the two warps that share a lane quarter (named barrier of 64
+//     threads) for the few values that cross the column halves; the V rows of a point are adjacent lanes of one warp,
+//     so the cross-view operations of the output stage (masked softmax, RGB blend) are warp shuffles.
+// V in {2, 4} (the rows of a point must not straddle a warp); other view counts use k_blend_tc.  Same arithmetic as
+// k_blend_tc (the same formulas in the same order per value), hence the same parity envelope.
+// =============================================================================================
+#define TM_GROUPS 3
+#define TM_EPI_WARPS 8
+#define TM_THREADS ((TM_GROUPS * TM_EPI_WARPS + 1) * 32)
+#define TM_AHI(g) ((uint32_t)(g) * 128u)
+#define TM_ALO(g) ((uint32_t)(g) * 128u + 32u)
+#define TM_D(g) ((uint32_t)(g) * 128u + 64u)
+
+struct TmGroup {
+  float X[19][BS];        // x19 = feat19 + direction feature
+  float A16[16][BS];      // rgb_fc.0 outputs crossing the halves
+  float RGB[3][BS];
+  float RD[4][BS];
+  float m[128], e[128], vis[128], part[128];
+};
+struct TmBars {
+  uint64_t a_ready[TM_GROUPS];
+  uint64_t d_full[TM_GROUPS];
+  uint32_t tmem_base;
+};
+#define SM_TM_WF W_TC_BYTES
+#define SM_TM_GRP ((SM_TM_WF + F_TOTAL * 4 + 127) / 128 * 128)
+#define SM_TM_BAR (SM_TM_GRP + TM_GROUPS * (int)sizeof(TmGroup))
+#define SM_TM_TOTAL (SM_TM_BAR + 128)
+
+// 16 values (consecutive k, k0 % 16 == 0) -> hi / lo words at TMEM columns k0/2 .. k0/2+7 of the A regions
+__device__ __forceinline__ void tm_store16(uint32_t t_hi, uint32_t t_lo, int k0, const float (&v)[16]) {
+  uint32_t hi[8], lo[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) tc::split2(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
+  tc::tmem_st8(t_hi + (k0 >> 1), hi);
+  tc::tmem_st8(t_lo + (k0 >> 1), lo);
+}
+__device__ __forceinline__ void tm_store8(uint32_t t_hi, uint32_t t_lo, int k0, const float (&v)[8]) {
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) tc::split2(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
+  tc::tmem_st4(t_hi + (k0 >> 1), hi);
+  tc::tmem_st4(t_lo + (k0 >> 1), lo);
+}
+// one layer: D[128 x N] = A[128 x K] (TMEM, hi | lo) * W^T (smem), issued by one thread
+template <int N, int KSTEPS>
+__device__ __forceinline__ void tm_issue(uint32_t tD, uint32_t a_hi, uint32_t a_lo, uint32_t w_addr, uint64_t* bar, bool fast) {
+  const uint32_t idesc = tc::idesc_f16(128, N, 0);
+  const uint64_t db = tc::smem_desc_kmajor(0, N * 16, 128);
+  const uint32_t bh = (uint32_t)(db >> 32);
+  const uint32_t b0 = (uint32_t)db | (w_addr >> 4);
+  constexpr uint32_t B_LO = (N * KSTEPS * 16 * 2) >> 4, B_KS = (N * 32) >> 4;
+#pragma unroll
+  for (int ks = 0; ks < KSTEPS; ++ks) {
+    if (ks == 0) tc::mma_ts_w<false>(tD, a_hi, b0, bh, idesc);
+    else tc::mma_ts_w<true>(tD, a_hi + ks * 8, b0 + ks * B_KS, bh, idesc);
+    if (!fast) tc::mma_ts_w<true>(tD, a_lo + ks * 8, b0 + ks * B_KS, bh, idesc);
+    if (!fast) tc::mma_ts_w<true>(tD, a_hi + ks * 8, b0 + B_LO + ks * B_KS, bh, idesc);
+  }
+  tc::mma_commit(bar);
+}
+
+template <int V>
+__global__ void __launch_bounds__(TM_THREADS, 1)
+k_blend_tm(const uint8_t* __restrict__ wtc, const float* __restrict__ wf32, float s_abs, const float* __restrict__ feat,
+           const float* __restrict__ rdiff, const uint8_t* __restrict__ mask, int packed19,
+           const int32_t* __restrict__ list, const int32_t* __restrict__ count, int64_t n, float* __restrict__ rgb_out,
+           uint8_t* __restrict__ views_out, int fast_i) {
+  const bool fast = fast_i != 0;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  TmBars* bars = reinterpret_cast<TmBars*>(smem + SM_TM_BAR);
+  const float* WF = reinterpret_cast<const float*>(smem + SM_TM_WF);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < W_TC_BYTES / 16; i += TM_THREADS)
+    reinterpret_cast<uint4*>(smem)[i] = reinterpret_cast<const uint4*>(wtc)[i];
+  for (int i = tid; i < F_TOTAL; i += TM_THREADS) reinterpret_cast<float*>(smem + SM_TM_WF)[i] = wf32[i];
+  if (warp == TM_GROUPS * TM_EPI_WARPS) tc::tmem_alloc<512>(&bars->tmem_base);
+  if (tid == 0) {
+    for (int g = 0; g < TM_GROUPS; ++g) {
+      tc::mbar_init(&bars->a_ready[g], TM_EPI_WARPS);
+      tc::mbar_init(&bars->d_full[g], 1);
+    }
+    tc::mbar_fence_init();
+  }
+  tc::fence_proxy_async();
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tbase = bars->tmem_base;
+
+  int64_t n_total = n;
+  if (count) {
+    const int64_t c = *count;
+    n_total = c < n_total ? c : n_total;
+  }
+  constexpr int ppt = BT_ROWS / V;
+  const int64_t n_tiles = (n_total + ppt - 1) / ppt;
+  const int64_t stride = (int64_t)gridDim.x * TM_GROUPS;
+
+  if (warp < TM_GROUPS * TM_EPI_WARPS) {
+    // =============================== epilogue warps ===============================
+    const int g = warp / TM_EPI_WARPS, lw = warp % TM_EPI_WARPS;
+    const int q = lw & 3, half = lw >> 2;
+    const int r = q * 32 + lane;
+    TmGroup& G = *reinterpret_cast<TmGroup*>(smem + SM_TM_GRP + g * sizeof(TmGroup));
+    const uint32_t tl = tbase + ((uint32_t)(q * 32) << 16);
+    const uint32_t t_hi = tl + TM_AHI(g), t_lo = tl + TM_ALO(g), t_d = tl + TM_D(g);
+    const int pair_bar = 1 + g * 4 + q;
+    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory"); };
+    auto signal = [&]() {           // my part of the next A operand is in TMEM
+      tc::tmem_wait_st();
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&bars->a_ready[g]);
+    };
+    uint32_t ph = 0;
+    auto wait_d = [&]() {
+      tc::mbar_wait(&bars->d_full[g], ph & 1);
+      ph++;
+      tc::tc_fence_after();
+    };
+    for (int64_t tile = (int64_t)blockIdx.x * TM_GROUPS + g; tile < n_tiles; tile += stride) {
+      // ---- record of my row: row r <-> (point tile*ppt + r / V, view r % V) ----
+      const int64_t rec_i = tile * BT_ROWS + r;
+      const bool ok = rec_i < n_total * V;
+      float rec[FEAT_REC];
+      float4 rd = make_float4(0.f, 0.f, 0.f, 1.f);
+#pragma unroll
+      for (int c = 0; c < FEAT_REC; ++c) rec[c] = 0.f;
+      if (ok) {
+        rd = reinterpret_cast<const float4*>(rdiff)[rec_i];
+        if (packed19) {
+          const float* f = feat + rec_i * 19;
+#pragma unroll
+          for (int c = 0; c < 19; ++c) rec[c] = f[c];
+          rec[19] = mask[rec_i] ? 1.0f : 0.0f;
+        } else {
+          const float4* f = reinterpret_cast<const float4*>(feat + rec_i * FEAT_REC);
+#pragma unroll
+          for (int c = 0; c < 5; ++c) {
+            const float4 t = f[c];
+            rec[4 * c] = t.x; rec[4 * c + 1] = t.y; rec[4 * c + 2] = t.z; rec[4 * c + 3] = t.w;
+          }
+        }
+      }
+      // ---- ray_dir_fc 4 -> 16 (both halves), 16 -> 19 split 10 / 9 ; x19 -> smem ----
+      {
+        float h16[16];
+#pragma unroll
+        for (int o = 0; o < 16; ++o) {
+          const float* w = WF + F_DIR0_W + o * 4;
+          h16[o] = bt_elu(fmaf(w[3], rd.w, fmaf(w[2], rd.z, fmaf(w[1], rd.y, fmaf(w[0], rd.x, WF[F_DIR0_B + o])))));
+        }
+        const int o0 = half ? 10 : 0, o1 = half ? 19 : 10;
+        for (int o = o0; o < o1; ++o) {
+          const float* w = WF + F_DIR1_W + o * 16;
+          float a = WF[F_DIR1_B + o];
+#pragma unroll
+          for (int k = 0; k < 16; ++k) a = fmaf(w[k], h16[k], a);
+          G.X[o][r] = rec[o] + bt_elu(a);
+        }
+      }
+      if (half == 0) {
+        G.RGB[0][r] = rec[0]; G.RGB[1][r] = rec[1]; G.RGB[2][r] = rec[2];
+        G.RD[0][r] = rd.x; G.RD[1][r] = rd.y; G.RD[2][r] = rd.z; G.RD[3][r] = rd.w;
+        G.m[r] = rec[19];
+        // pooling exponential, correctly rounded (see blend.cu / DESIGN.md §2)
+        const float arg = __fmul_rn(s_abs, __fsub_rn(rd.w, 1.0f));
+        G.e[r] = (float)exp((double)arg);
+      }
+      pair_sync();
+      // ---- pooling weights of my point (blending_network.py:76-80) ----
+      const int r0 = (r / V) * V;
+      float wvs[V];
+      {
+        float emin = INFINITY;
+#pragma unroll
+        for (int v = 0; v < V; ++v) emin = fminf(emin, G.e[r0 + v]);
+        float wsum = 0.f;
+#pragma unroll
+        for (int v = 0; v < V; ++v) wsum = __fadd_rn(wsum, __fmul_rn(__fsub_rn(G.e[r0 + v], emin), G.m[r0 + v]));
+        const float den = __fadd_rn(wsum, 1e-8f);
+#pragma unroll
+        for (int v = 0; v < V; ++v) wvs[v] = __fdiv_rn(__fmul_rn(__fsub_rn(G.e[r0 + v], emin), G.m[r0 + v]), den);
+      }
+      const float wv = wvs[r - r0];
+      const float mrow = G.m[r];
+      // ---- A operand of base_fc.0: [mean19, var19, x19, 0 x 7] ----
+      {
+        float vals[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) vals[k] = 0.f;
+        if (half == 0) {
+#pragma unroll
+          for (int c = 0; c < 19; ++c) {
+            float mean = 0.f;
+#pragma unroll
+            for (int v = 0; v < V; ++v) mean = fmaf(G.X[c][r0 + v], wvs[v], mean);
+            vals[c] = mean;
+            if (c < 13) {
+              float var = 0.f;
+#pragma unroll
+              for (int v = 0; v < V; ++v) {
+                const float d = G.X[c][r0 + v] - mean;
+                var = fmaf(wvs[v] * d, d, var);
+              }
+              vals[19 + c] = var;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int c = 13; c < 19; ++c) {
+            float mean = 0.f;
+#pragma unroll
+            for (int v = 0; v < V; ++v) mean = fmaf(G.X[c][r0 + v], wvs[v], mean);
+            float var = 0.f;
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+              const float d = G.X[c][r0 + v] - mean;
+              var = fmaf(wvs[v] * d, d, var);
+            }
+            vals[c - 13] = var;
+          }
+#pragma unroll
+          for (int c = 0; c < 19; ++c) vals[6 + c] = G.X[c][r];
+        }
+        float a[16], b[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) { a[k] = vals[k]; b[k] = vals[16 + k]; }
+        tm_store16(t_hi, t_lo, half * 32, a);
+        tm_store16(t_hi, t_lo, half * 32 + 16, b);
+      }
+      signal();
+      // ---- base_fc.0 : 57(64) -> 64, ELU ----
+      wait_d();
+#pragma unroll
+      for (int hb = 0; hb < 2; ++hb) {
+        uint32_t acc[16];
+        tc::tmem_ld16(t_d + half * 32 + hb * 16, acc);
+        tc::tmem_wait_ld();
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = bt_elu(__uint_as_float(acc[j]) + WF[F_BASE0_B + half * 32 + hb * 16 + j]);
+        tm_store16(t_hi, t_lo, half * 32 + hb * 16, v);
+      }
+      signal();
+      // ---- base_fc.2 : 64 -> 32, ELU -> x (registers) ; next A = x * pooling weight ----
+      float x[16];
+      wait_d();
+      {
+        uint32_t acc[16];
+        tc::tmem_ld16(t_d + half * 16, acc);
+        tc::tmem_wait_ld();
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          x[j] = bt_elu(__uint_as_float(acc[j]) + WF[F_BASE1_B + half * 16 + j]);
+          v[j] = x[j] * wv;
+        }
+        tm_store16(t_hi, t_lo, half * 16, v);
+      }
+      signal();
+      // ---- vis_fc.0 : 32 -> 32, ELU ----
+      wait_d();
+      {
+        uint32_t acc[16];
+        tc::tmem_ld16(t_d + half * 16, acc);
+        tc::tmem_wait_ld();
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = bt_elu(__uint_as_float(acc[j]) + WF[F_VIS0_B + half * 16 + j]);
+        tm_store16(t_hi, t_lo, half * 16, v);
+      }
+      signal();
+      // ---- vis_fc.2 : 32 -> 33, ELU ; x += x_res ; vis = sigmoid(.) * mask ; next A = x * vis ----
+      wait_d();
+      {
+        uint32_t acc[16];
+        tc::tmem_ld16(t_d + half * 16, acc);
+        if (half == 1) {
+          uint32_t extra;
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(extra) : "r"(t_d + 32));
+          tc::tmem_wait_ld();
+          G.vis[r] = bt_sigmoid(bt_elu(__uint_as_float(extra) + WF[F_VIS1_B + 32])) * mrow;
+        } else {
+          tc::tmem_wait_ld();
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) x[j] += bt_elu(__uint_as_float(acc[j]) + WF[F_VIS1_B + half * 16 + j]);
+        pair_sync();
+        const float vs = G.vis[r];
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = x[j] * vs;
+        tm_store16(t_hi, t_lo, half * 16, v);
+      }
+      signal();
+      // ---- vis_fc2.0 : 32 -> 32, ELU ; vis_fc2.2 : 32 -> 1, sigmoid * mask ; next A = [x, vis2, ray_diff, 0] ----
+      wait_d();
+      {
+        uint32_t acc[16];
+        tc::tmem_ld16(t_d + half * 16, acc);
+        tc::tmem_wait_ld();
+        float p = 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          p = fmaf(bt_elu(__uint_as_float(acc[j]) + WF[F_V20_B + half * 16 + j]), WF[F_V21_W + half * 16 + j], p);
+        if (half == 1) G.part[r] = p;
+        pair_sync();
+        tm_store16(t_hi, t_lo, half * 16, x);
+        if (half == 0) {
+          const float vis2 = bt_sigmoid(p + G.part[r] + WF[F_V21_B]) * mrow;
+          const float t[8] = {vis2, G.RD[0][r], G.RD[1][r], G.RD[2][r], G.RD[3][r], 0.f, 0.f, 0.f};
+          tm_store8(t_hi, t_lo, 32, t);
+        } else {
+          const float t[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          tm_store8(t_hi, t_lo, 40, t);
+        }
+      }
+      signal();
+      // ---- rgb_fc.0 : 37(48) -> 16, ELU ; rgb_fc.2/.4 : 16 -> 8 -> 1 ; masked softmax over the views ; blend ----
+      wait_d();
+      {
+        uint32_t acc[8];
+        tc::tmem_ld8(t_d + half * 8, acc);
+        tc::tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) G.A16[half * 8 + j][r] = bt_elu(__uint_as_float(acc[j]) + WF[F_RGB0_B + half * 8 + j]);
+        // the accumulator has been read: the group's next tile may start while the output stage runs
+        tc::tc_fence_before();
+        pair_sync();
+        if (half == 0) {
+          float a16[16];
+#pragma unroll
+          for (int k = 0; k < 16; ++k) a16[k] = G.A16[k][r];
+          float lg = WF[F_RGB2_B];
+#pragma unroll
+          for (int o = 0; o < 8; ++o) {
+            const float* w = WF + F_RGB1_W + o * 16;
+            float a = WF[F_RGB1_B + o];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) a = fmaf(w[k], a16[k], a);
+            lg = fmaf(bt_elu(a), WF[F_RGB2_W + o], lg);
+          }
+          // masked softmax over the V adjacent lanes of my point, in view order (blending_network.py:109-115)
+          const bool live = mrow > 0.f;
+          const float lgm = live ? lg : -1e9f;
+          float mx = lgm;
+#pragma unroll
+          for (int o = 1; o < V; o <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+          const float ex = expf(lgm - mx);
+          const int base_lane = lane - (lane % V);
+          float ssum = 0.f, cr = 0.f, cg = 0.f, cb = 0.f;
+          unsigned vbits = 0;
+#pragma unroll
+          for (int v = 0; v < V; ++v) {       // sequential over the views like the scalar loop of k_blend_tc
+            const float ev = __shfl_sync(0xffffffffu, ex, base_lane + v);
+            const unsigned lv = __shfl_sync(0xffffffffu, live ? 1u : 0u, base_lane + v);
+            vbits |= lv << v;
+            ssum += ev;
+            cr = fmaf(ev, G.RGB[0][r0 + v], cr);
+            cg = fmaf(ev, G.RGB[1][r0 + v], cg);
+            cb = fmaf(ev, G.RGB[2][r0 + v], cb);
+          }
+          if (r == r0) {
+            const int64_t i = tile * ppt + r / V;
+            if (i < n_total) {
+              const int64_t id = list ? (int64_t)list[i] : i;
+              const float inv = 1.0f / ssum;
+              rgb_out[id * 3] = cr * inv;
+              rgb_out[id * 3 + 1] = cg * inv;
+              rgb_out[id * 3 + 2] = cb * inv;
+              if (views_out) views_out[id] = (uint8_t)vbits;
+            }
+          }
+        }
+      }
+    }
+  } else {
+    // =============================== the MMA issuer ===============================
+    if (tc::elect_one()) {
+      const uint32_t w_a = tc::smem_u32(smem);
+      uint32_t ph[TM_GROUPS];
+#pragma unroll
+      for (int g = 0; g < TM_GROUPS; ++g) ph[g] = 0;
+      const int64_t first = (int64_t)blockIdx.x * TM_GROUPS;
+      for (int64_t base = first; base < n_tiles; base += stride) {
+#pragma unroll 1
+        for (int layer = 0; layer < 6; ++layer) {
+#pragma unroll
+          for (int g = 0; g < TM_GROUPS; ++g) {
+            if (base + g >= n_tiles) continue;
+            tc::mbar_wait(&bars->a_ready[g], ph[g] & 1);
+            ph[g]++;
+            tc::tc_fence_after();
+            const uint32_t tD = tbase + TM_D(g), ah = tbase + TM_AHI(g), al = tbase + TM_ALO(g);
+            switch (layer) {
+              case 0: tm_issue<64, 4>(tD, ah, al, w_a + W_BASE0, &bars->d_full[g], fast); break;
+              case 1: tm_issue<32, 4>(tD, ah, al, w_a + W_BASE1, &bars->d_full[g], fast); break;
+              case 2: tm_issue<32, 2>(tD, ah, al, w_a + W_VIS0, &bars->d_full[g], fast); break;
+              case 3: tm_issue<48, 2>(tD, ah, al, w_a + W_VIS1, &bars->d_full[g], fast); break;
+              case 4: tm_issue<32, 2>(tD, ah, al, w_a + W_V20, &bars->d_full[g], fast); break;
+              default: tm_issue<16, 3>(tD, ah, al, w_a + W_RGB0, &bars->d_full[g], fast); break;
+            }
+          }
+        }
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == TM_GROUPS * TM_EPI_WARPS) tc::tmem_dealloc<512>(tbase);
+}
+
 // ---------------------------------------------------------------------------------------------
 // host
 // ---------------------------------------------------------------------------------------------
@@ -542,6 +969,26 @@ int launch_blend_tc(const surf_net* n, const float* d_feat, const float* d_raydi
   }
   const int ppt = BT_ROWS / V;
   const int64_t tiles = (n_pts + ppt - 1) / ppt;
+  if (V == 2 || V == 4) {        // three tiles in flight per CTA, activations in TMEM, no block barriers
+    int rc = surf_ensure_dyn_smem((const void*)k_blend_tm<2>, SM_TM_TOTAL);
+    if (rc) return rc;
+    rc = surf_ensure_dyn_smem((const void*)k_blend_tm<4>, SM_TM_TOTAL);
+    if (rc) return rc;
+    const int64_t want = (tiles + TM_GROUPS - 1) / TM_GROUPS;
+    const int grid = (int)(want < n->n_sm ? want : n->n_sm);
+    surf_time_begin(3, st);
+    if (V == 2)
+      k_blend_tm<2><<<grid, TM_THREADS, SM_TM_TOTAL, st>>>(n->blend_tc_w, n->blend_tc_f, n->dev.blend_s, d_feat, d_raydiff,
+                                                          d_mask, packed19 ? 1 : 0, list, count, n_pts, d_rgb, d_views,
+                                                          fast ? 1 : 0);
+    else
+      k_blend_tm<4><<<grid, TM_THREADS, SM_TM_TOTAL, st>>>(n->blend_tc_w, n->blend_tc_f, n->dev.blend_s, d_feat, d_raydiff,
+                                                          d_mask, packed19 ? 1 : 0, list, count, n_pts, d_rgb, d_views,
+                                                          fast ? 1 : 0);
+    surf_time_end(3, st);
+    SURF_LAUNCH_CHECK();
+    return 0;
+  }
   const int64_t cap = (int64_t)n->n_sm * 2;
   const int grid = (int)(tiles < cap ? tiles : cap);
   surf_time_begin(3, st);

@@ -66,7 +66,7 @@ class ImplicitSurface(nn.Module):
         self._lin = None
         self._ws = None
         self.scene_cache = GLOBAL_SCENE_CACHE
-        self.ray_batch = 1 << 16        # rays per launch set in validate()
+        self.ray_batch = 1 << 15        # rays per launch set in validate(): 24-32 k is the measured optimum (tools/ray_batch_sweep.py)
         # MLP kernel family of every call made through this module (include/surf_b200.h SURF_MLP_*): the tcgen05
         # fp32-grade kernels by default; optional conf key ``mlp_mode`` (not a reference key) or assign the attribute
         mode = _lib.MLP_TC
