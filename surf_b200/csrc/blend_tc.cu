@@ -860,28 +860,39 @@ k_blend_tm(const uint8_t* __restrict__ wtc, const float* __restrict__ wf32, floa
     // =============================== the MMA issuer ===============================
     if (tc::elect_one()) {
       const uint32_t w_a = tc::smem_u32(smem);
+      // round robin over the groups: whichever has its next A operand ready gets its layer issued (a blocking wait on
+      // one group would hold back the MMAs of the other two)
       uint32_t ph[TM_GROUPS];
+      int layer[TM_GROUPS];
+      int64_t tile_of[TM_GROUPS];
+      int live = 0;
 #pragma unroll
-      for (int g = 0; g < TM_GROUPS; ++g) ph[g] = 0;
-      const int64_t first = (int64_t)blockIdx.x * TM_GROUPS;
-      for (int64_t base = first; base < n_tiles; base += stride) {
-#pragma unroll 1
-        for (int layer = 0; layer < 6; ++layer) {
+      for (int g = 0; g < TM_GROUPS; ++g) {
+        ph[g] = 0;
+        layer[g] = 0;
+        tile_of[g] = (int64_t)blockIdx.x * TM_GROUPS + g;
+        live += tile_of[g] < n_tiles ? 1 : 0;
+      }
+      while (live > 0) {
 #pragma unroll
-          for (int g = 0; g < TM_GROUPS; ++g) {
-            if (base + g >= n_tiles) continue;
-            tc::mbar_wait(&bars->a_ready[g], ph[g] & 1);
-            ph[g]++;
-            tc::tc_fence_after();
-            const uint32_t tD = tbase + TM_D(g), ah = tbase + TM_AHI(g), al = tbase + TM_ALO(g);
-            switch (layer) {
-              case 0: tm_issue<64, 4>(tD, ah, al, w_a + W_BASE0, &bars->d_full[g], fast); break;
-              case 1: tm_issue<32, 4>(tD, ah, al, w_a + W_BASE1, &bars->d_full[g], fast); break;
-              case 2: tm_issue<32, 2>(tD, ah, al, w_a + W_VIS0, &bars->d_full[g], fast); break;
-              case 3: tm_issue<48, 2>(tD, ah, al, w_a + W_VIS1, &bars->d_full[g], fast); break;
-              case 4: tm_issue<32, 2>(tD, ah, al, w_a + W_V20, &bars->d_full[g], fast); break;
-              default: tm_issue<16, 3>(tD, ah, al, w_a + W_RGB0, &bars->d_full[g], fast); break;
-            }
+        for (int g = 0; g < TM_GROUPS; ++g) {
+          if (tile_of[g] >= n_tiles) continue;
+          if (!tc::mbar_try_wait(&bars->a_ready[g], ph[g] & 1)) continue;
+          ph[g]++;
+          tc::tc_fence_after();
+          const uint32_t tD = tbase + TM_D(g), ah = tbase + TM_AHI(g), al = tbase + TM_ALO(g);
+          switch (layer[g]) {
+            case 0: tm_issue<64, 4>(tD, ah, al, w_a + W_BASE0, &bars->d_full[g], fast); break;
+            case 1: tm_issue<32, 4>(tD, ah, al, w_a + W_BASE1, &bars->d_full[g], fast); break;
+            case 2: tm_issue<32, 2>(tD, ah, al, w_a + W_VIS0, &bars->d_full[g], fast); break;
+            case 3: tm_issue<48, 2>(tD, ah, al, w_a + W_VIS1, &bars->d_full[g], fast); break;
+            case 4: tm_issue<32, 2>(tD, ah, al, w_a + W_V20, &bars->d_full[g], fast); break;
+            default: tm_issue<16, 3>(tD, ah, al, w_a + W_RGB0, &bars->d_full[g], fast); break;
+          }
+          if (++layer[g] == 6) {
+            layer[g] = 0;
+            tile_of[g] += stride;
+            if (tile_of[g] >= n_tiles) --live;
           }
         }
       }

@@ -12,21 +12,27 @@
 // where g_pe / g_feat collect the PE (lin0 + skip layer) and feature columns of ga, gd_* those of gad, Jd_pe is the
 // derivative of the PE Jacobian along v (-f^2 sin / -f^2 cos) and Jd_feat the mixed second derivatives of the
 // trilinear interpolant (the pure second derivatives vanish).
-// 8 points per 128-thread block, thread = output neuron (forward) / input column (reverse), everything of the 8 points
+// 16 points per 256-thread block (thread = (neuron, point half): 8 points each, so a weight read from L2 feeds 16
+// points), thread = output neuron (forward) / input column (reverse), everything of the 16 points
 // in shared memory, weights read from L2 (k-major for the forward, row-major for the reverse: both coalesced).
 #include <vector>
 
 #include "surf_internal.cuh"
 
-#define SM_NP 8
-#define SM_THREADS 128
+#define SM_NP 16             // points per block iteration
+#define SM_PH 8              // points per thread (two thread halves of 128 share the weights)
+#define SM_THREADS 256
+#define SM_PS 20              // row stride of the k-major operands
 #define SM_STRIDE 160
 
 struct SmoothSmem {
-  float A[SM_NP][SM_STRIDE], Ad[SM_NP][SM_STRIDE];
+  // GEMV operands k-major with the 16 points innermost (row stride SM_PS floats, 16-byte aligned): a thread reads its 8
+  // points of one k as two 128-bit broadcast loads (a [point][k] layout costs 16 scalar broadcasts per k and made the
+  // kernel shared-memory-bandwidth bound: 5.6 ms for 70 k points)
+  float A[SM_STRIDE][SM_PS], Ad[SM_STRIDE][SM_PS];
   float Z[6][SM_NP][128], Zd[6][SM_NP][128];
-  float GA[SM_NP][SM_STRIDE], GAd[SM_NP][SM_STRIDE];
-  float D[SM_NP][128], Dd[SM_NP][128];
+  float GA[SM_STRIDE][SM_PS], GAd[SM_STRIDE][SM_PS];
+  float D[128][SM_PS], Dd[128][SM_PS];
   float PE[SM_NP][28], PEd[SM_NP][28], FT[SM_NP][28], FTd[SM_NP][28];
   float gpe[SM_NP][28], gdpe[SM_NP][28], gft[SM_NP][28], gdft[SM_NP][28];
   float pt[SM_NP][3];
@@ -121,6 +127,7 @@ k_sdf_smooth(const DevScene sc, const DevNet net, const float* __restrict__ wk, 
   extern __shared__ __align__(16) uint8_t smem_raw[];
   SmoothSmem& S = *reinterpret_cast<SmoothSmem*>(smem_raw);
   const int tid = threadIdx.x;
+  const int nid = tid & 127, pb = (tid >> 7) * SM_PH;     // my neuron / column, my first point
   const int pe_dim = net.pe_dim;       // 27
   for (int64_t base = (int64_t)blockIdx.x * SM_NP; base < n; base += (int64_t)gridDim.x * SM_NP) {
     // a group of points none of which is evaluated (masked-out samples of a ray): zeros, no work
@@ -166,8 +173,8 @@ k_sdf_smooth(const DevScene sc, const DevNet net, const float* __restrict__ wk, 
     }
     __syncthreads();
     for (int i = tid; i < SM_NP * pe_dim; i += SM_THREADS) {
-      S.A[i / pe_dim][i % pe_dim] = S.PE[i / pe_dim][i % pe_dim];
-      S.Ad[i / pe_dim][i % pe_dim] = S.PEd[i / pe_dim][i % pe_dim];
+      S.A[i % pe_dim][i / pe_dim] = S.PE[i / pe_dim][i % pe_dim];
+      S.Ad[i % pe_dim][i / pe_dim] = S.PEd[i / pe_dim][i % pe_dim];
     }
     __syncthreads();
     // ---- forward with tangent ----
@@ -175,38 +182,51 @@ k_sdf_smooth(const DevScene sc, const DevNet net, const float* __restrict__ wk, 
     for (int l = 0; l < 6; ++l) {
       const int od = net.out_dim[l];
       const float* W = wk + wk_off[l];
-      float acc[SM_NP], accd[SM_NP];
+      float acc[SM_PH], accd[SM_PH];
 #pragma unroll
-      for (int p = 0; p < SM_NP; ++p) { acc[p] = 0.f; accd[p] = 0.f; }
-      if (tid < od) {
-        for (int k = 0; k < in_dim; ++k) {
-          const float w = W[(size_t)k * SM_STRIDE + tid];
+      for (int p = 0; p < SM_PH; ++p) { acc[p] = 0.f; accd[p] = 0.f; }
+      if (nid < od) {
+        // eight weight loads in flight per thread (the weights come from L2: one block per SM, 8 warps — a load per
+        // iteration leaves the warp waiting on L2 latency)
+        for (int k0 = 0; k0 < in_dim; k0 += 8) {
+          float w8[8];
 #pragma unroll
-          for (int p = 0; p < SM_NP; ++p) { acc[p] = fmaf(S.A[p][k], w, acc[p]); accd[p] = fmaf(S.Ad[p][k], w, accd[p]); }
+          for (int j = 0; j < 8; ++j) w8[j] = (k0 + j < in_dim) ? __ldg(W + (size_t)(k0 + j) * SM_STRIDE + nid) : 0.f;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int k = (k0 + j < in_dim) ? k0 + j : 0;
+            const float w = w8[j];
+            const float4 a0 = *reinterpret_cast<const float4*>(&S.A[k][pb]), a1 = *reinterpret_cast<const float4*>(&S.A[k][pb + 4]);
+            const float4 d0 = *reinterpret_cast<const float4*>(&S.Ad[k][pb]), d1 = *reinterpret_cast<const float4*>(&S.Ad[k][pb + 4]);
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float dv[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+            for (int p = 0; p < SM_PH; ++p) { acc[p] = fmaf(av[p], w, acc[p]); accd[p] = fmaf(dv[p], w, accd[p]); }
+          }
         }
-        const float b = W[(size_t)in_dim * SM_STRIDE + tid];
+        const float b = W[(size_t)in_dim * SM_STRIDE + nid];
 #pragma unroll
-        for (int p = 0; p < SM_NP; ++p) { S.Z[l][p][tid] = acc[p] + b; S.Zd[l][p][tid] = accd[p]; }
+        for (int p = 0; p < SM_PH; ++p) { S.Z[l][pb + p][nid] = acc[p] + b; S.Zd[l][pb + p][nid] = accd[p]; }
       } else {
 #pragma unroll
-        for (int p = 0; p < SM_NP; ++p) { S.Z[l][p][tid] = 0.f; S.Zd[l][p][tid] = 0.f; }
+        for (int p = 0; p < SM_PH; ++p) { S.Z[l][pb + p][nid] = 0.f; S.Zd[l][pb + p][nid] = 0.f; }
       }
       __syncthreads();
       // next input [h | PE at the skip layer | features] and its tangent
-      for (int p = 0; p < SM_NP; ++p) {
+      for (int p = pb; p < pb + SM_PH; ++p) {
         float h = 0.f, hd = 0.f;
-        if (tid < od) {
+        if (nid < od) {
           float d1, d2;
-          sm_softplus(S.Z[l][p][tid], h, d1, d2);
-          hd = d1 * S.Zd[l][p][tid];
-        } else if (l + 1 == net.skip_layer && tid < od + pe_dim) {
-          h = S.PE[p][tid - od]; hd = S.PEd[p][tid - od];
+          sm_softplus(S.Z[l][p][nid], h, d1, d2);
+          hd = d1 * S.Zd[l][p][nid];
+        } else if (l + 1 == net.skip_layer && nid < od + pe_dim) {
+          h = S.PE[p][nid - od]; hd = S.PEd[p][nid - od];
         }
-        S.A[p][tid] = h; S.Ad[p][tid] = hd;
+        S.A[nid][p] = h; S.Ad[nid][p] = hd;
       }
       for (int i = tid; i < SM_NP * 28; i += SM_THREADS) {
-        S.A[i / 28][128 + i % 28] = S.FT[i / 28][i % 28];
-        S.Ad[i / 28][128 + i % 28] = S.FTd[i / 28][i % 28];
+        S.A[128 + i % 28][i / 28] = S.FT[i / 28][i % 28];
+        S.Ad[128 + i % 28][i / 28] = S.FTd[i / 28][i % 28];
       }
       in_dim = 128 + 28;
       __syncthreads();
@@ -214,10 +234,10 @@ k_sdf_smooth(const DevScene sc, const DevNet net, const float* __restrict__ wk, 
     // ---- reverse with tangent: ga_6 = row 0 of lin6 / scale, gad_6 = 0 ----
     {
       const float* W6 = wr + wr_off[6];
-      for (int k = tid; k < SM_STRIDE; k += SM_THREADS) {
+      for (int k = nid; k < SM_STRIDE; k += 128) {
         const float w = k < 156 ? W6[k] * net.inv_scale : 0.f;
 #pragma unroll
-        for (int p = 0; p < SM_NP; ++p) { S.GA[p][k] = w; S.GAd[p][k] = 0.f; }
+        for (int p = 0; p < SM_PH; ++p) { S.GA[k][pb + p] = w; S.GAd[k][pb + p] = 0.f; }
       }
     }
     __syncthreads();
@@ -225,48 +245,59 @@ k_sdf_smooth(const DevScene sc, const DevNet net, const float* __restrict__ wk, 
       const int od = net.out_dim[l];
       // feature columns of ga_{l+1}, PE columns of the skip layer's input
       for (int i = tid; i < SM_NP * 28; i += SM_THREADS) {
-        S.gft[i / 28][i % 28] += S.GA[i / 28][128 + i % 28];
-        S.gdft[i / 28][i % 28] += S.GAd[i / 28][128 + i % 28];
+        S.gft[i / 28][i % 28] += S.GA[128 + i % 28][i / 28];
+        S.gdft[i / 28][i % 28] += S.GAd[128 + i % 28][i / 28];
       }
       if (l + 1 == net.skip_layer)
         for (int i = tid; i < SM_NP * pe_dim; i += SM_THREADS) {
-          S.gpe[i / pe_dim][i % pe_dim] += S.GA[i / pe_dim][od + i % pe_dim];
-          S.gdpe[i / pe_dim][i % pe_dim] += S.GAd[i / pe_dim][od + i % pe_dim];
+          S.gpe[i / pe_dim][i % pe_dim] += S.GA[od + i % pe_dim][i / pe_dim];
+          S.gdpe[i / pe_dim][i % pe_dim] += S.GAd[od + i % pe_dim][i / pe_dim];
         }
       // delta_l and its tangent
-      for (int p = 0; p < SM_NP; ++p) {
+      for (int p = pb; p < pb + SM_PH; ++p) {
         float dl = 0.f, dd = 0.f;
-        if (tid < od) {
+        if (nid < od) {
           float h, d1, d2;
-          sm_softplus(S.Z[l][p][tid], h, d1, d2);
-          dl = S.GA[p][tid] * d1;
-          dd = S.GAd[p][tid] * d1 + S.GA[p][tid] * d2 * S.Zd[l][p][tid];
+          sm_softplus(S.Z[l][p][nid], h, d1, d2);
+          dl = S.GA[nid][p] * d1;
+          dd = S.GAd[nid][p] * d1 + S.GA[nid][p] * d2 * S.Zd[l][p][nid];
         }
-        S.D[p][tid] = dl; S.Dd[p][tid] = dd;
+        S.D[nid][p] = dl; S.Dd[nid][p] = dd;
       }
       __syncthreads();
       const int I = (l == 0) ? pe_dim : 156;
       const float* W = wr + wr_off[l];
-      for (int k = tid; k < SM_STRIDE; k += SM_THREADS) {
-        float ga[SM_NP], gad[SM_NP];
+      for (int k = nid; k < SM_STRIDE; k += 128) {
+        float ga[SM_PH], gad[SM_PH];
 #pragma unroll
-        for (int p = 0; p < SM_NP; ++p) { ga[p] = 0.f; gad[p] = 0.f; }
+        for (int p = 0; p < SM_PH; ++p) { ga[p] = 0.f; gad[p] = 0.f; }
         if (k < I) {
-          for (int o = 0; o < od; ++o) {
-            const float w = W[(size_t)o * SM_STRIDE + k];
+          for (int o0 = 0; o0 < od; o0 += 8) {
+            float w8[8];
 #pragma unroll
-            for (int p = 0; p < SM_NP; ++p) { ga[p] = fmaf(S.D[p][o], w, ga[p]); gad[p] = fmaf(S.Dd[p][o], w, gad[p]); }
+            for (int j = 0; j < 8; ++j) w8[j] = (o0 + j < od) ? __ldg(W + (size_t)(o0 + j) * SM_STRIDE + k) : 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int o = (o0 + j < od) ? o0 + j : 0;
+              const float w = w8[j];
+              const float4 a0 = *reinterpret_cast<const float4*>(&S.D[o][pb]), a1 = *reinterpret_cast<const float4*>(&S.D[o][pb + 4]);
+              const float4 d0 = *reinterpret_cast<const float4*>(&S.Dd[o][pb]), d1 = *reinterpret_cast<const float4*>(&S.Dd[o][pb + 4]);
+              const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+              const float dv[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+              for (int p = 0; p < SM_PH; ++p) { ga[p] = fmaf(av[p], w, ga[p]); gad[p] = fmaf(dv[p], w, gad[p]); }
+            }
           }
         }
 #pragma unroll
-        for (int p = 0; p < SM_NP; ++p) { S.GA[p][k] = ga[p]; S.GAd[p][k] = gad[p]; }
+        for (int p = 0; p < SM_PH; ++p) { S.GA[k][pb + p] = ga[p]; S.GAd[k][pb + p] = gad[p]; }
       }
       __syncthreads();
     }
     // lin0's input is the positional encoding
     for (int i = tid; i < SM_NP * pe_dim; i += SM_THREADS) {
-      S.gpe[i / pe_dim][i % pe_dim] += S.GA[i / pe_dim][i % pe_dim];
-      S.gdpe[i / pe_dim][i % pe_dim] += S.GAd[i / pe_dim][i % pe_dim];
+      S.gpe[i / pe_dim][i % pe_dim] += S.GA[i % pe_dim][i / pe_dim];
+      S.gdpe[i / pe_dim][i % pe_dim] += S.GAd[i % pe_dim][i / pe_dim];
     }
     __syncthreads();
     // ---- d/dx: feature part per (point, level), PE part per point ----
@@ -284,7 +315,7 @@ k_sdf_smooth(const DevScene sc, const DevNet net, const float* __restrict__ wk, 
         om3[0] *= inv * inv; om3[1] *= inv * inv; om3[2] *= inv * inv;
       }
       for (int d = 0; d < 3; ++d) S.part[p][lv][d] = od3[d] + om3[d];
-      if (grad_out) for (int d = 0; d < 3; ++d) S.D[p][lv * 3 + d] = o3[d];
+      if (grad_out) for (int d = 0; d < 3; ++d) S.D[lv * 3 + d][p] = o3[d];
     }
     __syncthreads();
     if (tid < SM_NP * 3) {
@@ -308,7 +339,7 @@ k_sdf_smooth(const DevScene sc, const DevNet net, const float* __restrict__ wk, 
         const bool on = flags == nullptr || ((flags[i] >> 1) & 1);
         smooth_out[i * 3 + d] = on ? fmaf(s2, net.scale, feat2) : 0.f;
         if (grad_out) {
-          const float feat1 = S.D[p][d] + S.D[p][3 + d] + S.D[p][6 + d] + S.D[p][9 + d];
+          const float feat1 = S.D[d][p] + S.D[3 + d][p] + S.D[6 + d][p] + S.D[9 + d][p];
           grad_out[i * 3 + d] = on ? fmaf(g1, net.scale, feat1) : 0.f;
         }
       }
