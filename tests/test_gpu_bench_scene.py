@@ -273,3 +273,22 @@ def test_index_table_beyond_2_31_entries():
     assert float(want.abs().max()) > 0.05
     assert_close(got, want, 1e-5, "sparse gather above 2^31 linear addresses")
     ps.destroy()
+
+
+# ------------------------------------------------------------------------------------------------
+# other view counts: V = 3 and V = 1 source views run the block-synchronous blending kernel (k_blend_tc), V = 2 / 4 the
+# TMEM-resident one (k_blend_tm); the goldens only hold V = 2 and V = 4
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("nv", [4, 2])
+def test_other_view_counts_vs_oracle(nv):
+    sc = synthetic.make_scene(nv, 96, 128, 16, seed=30 + nv, device=DEV)
+    m = bench_net()
+    ps = m.prepare(sc.matching_volume, sc.volumes, sc.sparse_idxes, sc.mask_volumes, sc.imgs, sc.features, sc.intrs, sc.c2ws)
+    sc_cpu = sc.to("cpu")
+    del sc
+    net = oracle_of(m)
+    o, d = synthetic.random_pixel_rays(sc_cpu, 256, seed=5)
+    t = torch.rand(256, 4, generator=torch.Generator().manual_seed(6))
+    r = compare_chunk(m, net, ps, sc_cpu, o, d, t, "nv=%d: " % nv, min_rows=0.8)
+    print("nv=%d parity:" % nv, r)
+    ps.destroy()
