@@ -54,6 +54,8 @@ def parse():
     ap.add_argument("--grid", type=int, default=GRID_RES, help="SDF grid resolution (0 = skip)")
     ap.add_argument("--cpu-rays", type=int, default=8192, help="rays per CPU-baseline sample / reference-arm step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--color-path", type=int, default=0, choices=[0, 1, 2],
+                    help="A/B: 0 gather then blend (default), 1 gather beside the SDF kernel, 2 gather fused into the blend")
     ap.add_argument("--scaling", default="strong", choices=["weak", "strong"],
                     help="N > 1: strong = one image ray-sharded + NCCL all-gather (default); weak = one image per rank")
     ap.add_argument("--mlp-mode", type=int, default=1, choices=[0, 1, 4],
@@ -401,6 +403,7 @@ def run_gpu(args):
     sc = synthetic.make_scene(args.views, args.height, args.width, args.base, seed=1, device=dev)
     m = build_net(dev)
     m.mlp_mode = args.mlp_mode
+    m.color_path = int(args.color_path)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     ps = m.prepare(sc.matching_volume, sc.volumes, sc.sparse_idxes, sc.mask_volumes, sc.imgs, sc.features, sc.intrs, sc.c2ws)
@@ -545,7 +548,9 @@ def run_gpu(args):
             others[name] = {"bound": bound, "ms": kernel_ms[kind], "achieved": ach, "peak": peak,
                             "unit": "GB/s" if bound == "hbm" else "TFLOP/s", "frac": ach / peak}
 
-    add("blend", "k_blend_tc" if tc else "k_blend", "tensor", n_eval * V * FLOP_BLEND_PER_POINT_VIEW, 1e12, pk["bf16_tflops"])
+    fused = tc and V in (2, 4) and args.color_path == 2
+    add("blend", ("k_blend_tm<FUSED> (projection gather + blending MLP in one kernel)" if fused else
+                  "k_blend_tm" if tc and V in (2, 4) else "k_blend_tc" if tc else "k_blend"), "tensor", n_eval * V * FLOP_BLEND_PER_POINT_VIEW, 1e12, pk["bf16_tflops"])
     add("lookup_feature", "k_lookup_feature", "hbm", n_eval * V * 304.0, 1e9, pk["hbm_gbs"])
     add("sample_rays", "k_sample_rays", "hbm", my_n * 8192.0, 1e9, pk["hbm_gbs"])
     add("point_flags", "k_point_flags", "hbm", P_all * 21.0, 1e9, pk["hbm_gbs"])

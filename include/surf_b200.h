@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define SURF_ABI_VERSION 3
+#define SURF_ABI_VERSION 4
 #define SURF_MAX_LEVELS 4
 #define SURF_MAX_VIEWS 8       /* source views (nv-1) */
 #define SURF_MAX_STAGES 4
@@ -136,6 +136,13 @@ void surf_net_destroy(surf_net* n);
 #define SURF_MLP_TC_FAST 4
 
 /* ---- render configuration (confs/surf.conf: model.implicit_surface.render) ---------------- */
+/* surf_render_cfg.color_path: how the projection gather and the blending network of a call are scheduled.  All three
+ * give the same results bit for bit (tests/test_gpu_bench_scene.py); measured on the 576x800 image:
+ * SERIAL 123.3 ms, OVERLAP 122.3 ms (the SDF kernel slows by what the gather gains), FUSED 126.6 ms. */
+#define SURF_COLOR_SERIAL 0   /* gather kernel, then blending kernel, on the caller's stream (default) */
+#define SURF_COLOR_OVERLAP 1  /* gather kernel on a library-owned side stream beside the SDF kernel, joined before the blend */
+#define SURF_COLOR_FUSED 2    /* gather inside the blending kernel (tensor-core modes, 2 or 4 source views; else SERIAL) */
+
 typedef struct surf_render_cfg {
   int32_t n_stages;                        /* 4 */
   int32_t n_samples[SURF_MAX_STAGES];      /* 64,32,24,16 */
@@ -149,6 +156,8 @@ typedef struct surf_render_cfg {
                                               concatenated (host-generated: linspace is not reproducible by
                                               a device formula) */
   int32_t mlp_mode;                        /* SURF_MLP_* kernel family for the SDF / blending MLPs of THIS call */
+  int32_t color_path;                      /* SURF_COLOR_*: how the projection gather and the blending network of this
+                                              call are scheduled (same results bit for bit) */
 } surf_render_cfg;
 
 /* Outputs of render_core; any pointer may be NULL (not written).  Shapes use B rays, S samples,

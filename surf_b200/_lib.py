@@ -14,7 +14,8 @@ MAX_LEVELS = 4
 MAX_VIEWS = 8
 MAX_STAGES = 4
 SDF_LAYERS = 7
-ABI_VERSION = 3
+ABI_VERSION = 4
+COLOR_SERIAL, COLOR_OVERLAP, COLOR_FUSED = 0, 1, 2   # surf_render_cfg.color_path
 
 # MLP kernel family, chosen per call (include/surf_b200.h SURF_MLP_*)
 MLP_FFMA = 0        # fp32 CUDA-core kernels: the parity anchor
@@ -116,6 +117,7 @@ class RenderCfg(C.Structure):
         ("chunk_rays", C.c_int32),
         ("d_lin_tables", C.c_void_p),
         ("mlp_mode", C.c_int32),
+        ("color_path", C.c_int32),
     ]
 
 

@@ -10,24 +10,8 @@
 
 #include <vector>
 
+#include "lookup_common.cuh"
 #include "surf_internal.cuh"
-
-#define FEAT_REC 20   // internal record per (point, view): 19 channels + validity flag
-
-__device__ __forceinline__ void bilinear_taps(float x, float y, int w, int h, int& x0, int& y0, float& tx, float& ty,
-                                              bool& ok) {
-  // grid = x / ((w-1)/2) - 1 (projector.py:533), sampled with align_corners=False (:544)
-  const float gx = x / ((float)(w - 1) * 0.5f) - 1.0f;
-  const float gy = y / ((float)(h - 1) * 0.5f) - 1.0f;
-  const float ix = (gx + 1.0f) * ((float)w * 0.5f) - 0.5f;
-  const float iy = (gy + 1.0f) * ((float)h * 0.5f) - 0.5f;
-  const float fx = floorf(ix), fy = floorf(iy);
-  ok = (fx >= -1.f) && (fx < (float)w) && (fy >= -1.f) && (fy < (float)h);   // false for NaN / far away
-  x0 = ok ? (int)fx : 0;
-  y0 = ok ? (int)fy : 0;
-  tx = ix - fx;
-  ty = iy - fy;
-}
 
 // one thread per (point, source view)
 __global__ void __launch_bounds__(256, 4)
@@ -54,63 +38,10 @@ k_lookup_feature(const DevScene sc, const PointSource src, float* __restrict__ f
       py = ray_at(src.rays_o[r * 3 + 1], src.rays_d[r * 3 + 1], t);
       pz = ray_at(src.rays_o[r * 3 + 2], src.rays_d[r * 3 + 2], t);
     }
-    // ---- compute_angle (projector.py:485-498) ----
-    float ax = sc.refcen[0] - px, ay = sc.refcen[1] - py, az = sc.refcen[2] - pz;
-    float inv = 1.0f / (sqrtf(ax * ax + ay * ay + az * az) + 1e-6f);
-    ax *= inv; ay *= inv; az *= inv;
-    float bx = sc.cen[v][0] - px, by = sc.cen[v][1] - py, bz = sc.cen[v][2] - pz;
-    inv = 1.0f / (sqrtf(bx * bx + by * by + bz * bz) + 1e-6f);
-    bx *= inv; by *= inv; bz *= inv;
-    const float ddx = ax - bx, ddy = ay - by, ddz = az - bz;
-    const float dn = fmaxf(sqrtf(ddx * ddx + ddy * ddy + ddz * ddz), 1e-6f);
-    const float dot = ax * bx + ay * by + az * bz;
-    // ---- projection ----
-    const float* M = sc.w2c[v];
-    const float cx = M[0] * px + M[1] * py + M[2] * pz + M[3];
-    const float cy = M[4] * px + M[5] * py + M[6] * pz + M[7];
-    const float cz = M[8] * px + M[9] * py + M[10] * pz + M[11];
-    const float* K = sc.K[v];
-    const float w = K[6] * cx + K[7] * cy + K[8] * cz;
     float rec[FEAT_REC];
-    bool valid = w > 0.f;
-    float scale = 1.0f;
-#pragma unroll
-    for (int lv = 0; lv < 4; ++lv) {
-      const int fw = sc.fw[lv], fh = sc.fh[lv];
-      const float u = (K[0] * scale) * cx + (K[1] * scale) * cy + (K[2] * scale) * cz;
-      const float vv = (K[3] * scale) * cx + (K[4] * scale) * cy + (K[5] * scale) * cz;
-      const float x = u / w, y = vv / w;
-      valid = valid && (x >= 0.f) && (x < (float)fw) && (y >= 0.f) && (y < (float)fh);
-      int x0, y0;
-      float tx, ty;
-      bool ok;
-      bilinear_taps(x, y, fw, fh, x0, y0, tx, ty, ok);
-      float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-      if (ok) {
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const int xi = x0 + (c & 1), yi = y0 + (c >> 1);
-          if (xi < 0 || xi >= fw || yi < 0 || yi >= fh) continue;
-          const float wgt = ((c & 1) ? tx : 1.f - tx) * ((c & 2) ? ty : 1.f - ty);
-          const size_t texel = ((size_t)(v + 1) * fh + yi) * fw + xi;
-          if (lv == 0) {
-            const float4 t0 = __ldg(sc.img0 + texel * 2), t1 = __ldg(sc.img0 + texel * 2 + 1);
-            a.x += t0.x * wgt; a.y += t0.y * wgt; a.z += t0.z * wgt; a.w += t0.w * wgt;
-            b.x += t1.x * wgt; b.y += t1.y * wgt; b.z += t1.z * wgt;
-          } else {
-            const float4 t0 = __ldg(sc.feat[lv] + texel);
-            a.x += t0.x * wgt; a.y += t0.y * wgt; a.z += t0.z * wgt; a.w += t0.w * wgt;
-          }
-        }
-      }
-      if (lv == 0) {
-        rec[0] = a.x; rec[1] = a.y; rec[2] = a.z; rec[3] = a.w; rec[4] = b.x; rec[5] = b.y; rec[6] = b.z;
-      } else {
-        rec[3 + 4 * lv] = a.x; rec[4 + 4 * lv] = a.y; rec[5 + 4 * lv] = a.z; rec[6 + 4 * lv] = a.w;
-      }
-      scale *= 0.5f;
-    }
-    rec[19] = valid ? 1.0f : 0.0f;
+    float4 rd;
+    lookup_row(sc, px, py, pz, v, rec, rd);
+    const bool valid = rec[19] > 0.f;
     if (packed19) {
       float* o = feat_out + it * 19;
 #pragma unroll
@@ -121,7 +52,7 @@ k_lookup_feature(const DevScene sc, const PointSource src, float* __restrict__ f
 #pragma unroll
       for (int c = 0; c < 5; ++c) o[c] = make_float4(rec[4 * c], rec[4 * c + 1], rec[4 * c + 2], rec[4 * c + 3]);
     }
-    reinterpret_cast<float4*>(rd_out)[it] = make_float4(ddx / dn, ddy / dn, ddz / dn, dot);
+    reinterpret_cast<float4*>(rd_out)[it] = rd;
   }
 }
 
@@ -515,12 +446,16 @@ static int cap_blocks(int64_t n, int per_block, int per_sm) {
 }
 
 int launch_lookup_feature(const surf_scene* s, const PointSource& src, float* d_feat, float* d_raydiff,
-                          uint8_t* d_mask, bool packed19, cudaStream_t st) {
+                          uint8_t* d_mask, bool packed19, cudaStream_t st, bool small_blocks) {
   SURF_CHECK_ARG(s->dev.img0, "scene has no images / feature maps");
   if (src.n <= 0 || s->dev.V <= 0) return 0;
   surf_time_begin(2, st);
-  k_lookup_feature<<<cap_blocks(src.n * s->dev.V, 256, 8), 256, 0, st>>>(s->dev, src, d_feat, d_raydiff, d_mask,
-                                                                         packed19 ? 1 : 0);
+  if (small_blocks)     // 128 threads x 64 registers: fits in the registers the persistent SDF kernel leaves free
+    k_lookup_feature<<<cap_blocks(src.n * s->dev.V, 128, 16), 128, 0, st>>>(s->dev, src, d_feat, d_raydiff, d_mask,
+                                                                            packed19 ? 1 : 0);
+  else
+    k_lookup_feature<<<cap_blocks(src.n * s->dev.V, 256, 8), 256, 0, st>>>(s->dev, src, d_feat, d_raydiff, d_mask,
+                                                                           packed19 ? 1 : 0);
   surf_time_end(2, st);
   SURF_LAUNCH_CHECK();
   return 0;

@@ -12,13 +12,13 @@
 
 #include <vector>
 
+#include "lookup_common.cuh"
 #include "surf_internal.cuh"
 #include "tc_common.cuh"
 
 #define BT_THREADS 256
 #define BT_ROWS 128
 #define BS 132                      // row stride (floats) of the k-major fp32 buffers
-#define FEAT_REC 20
 
 // ---- shared memory map (bytes) ----
 // tensor-core weights: [hi | lo] per layer, canonical K-major, (k8 group g, n) at g * N * 16 + n * 16
@@ -486,6 +486,8 @@ k_blend_tc(const uint8_t* __restrict__ wtc, const float* __restrict__ wf32, floa
 #define TM_GROUPS 3
 #define TM_EPI_WARPS 8
 #define TM_THREADS ((TM_GROUPS * TM_EPI_WARPS + 1) * 32)
+#define TMF_THREADS (TM_THREADS + TM_GROUPS * 32)   // fused edition: + one projection-gather warp per group
+#define TM_REC_CH 24                                // staged record per row: 20 (FEAT_REC) + ray_diff 4
 #define TM_AHI(g) ((uint32_t)(g) * 128u)
 #define TM_ALO(g) ((uint32_t)(g) * 128u + 32u)
 #define TM_D(g) ((uint32_t)(g) * 128u + 64u)
@@ -500,12 +502,18 @@ struct TmGroup {
 struct TmBars {
   uint64_t a_ready[TM_GROUPS];
   uint64_t d_full[TM_GROUPS];
+  uint64_t rec_full[TM_GROUPS * 2];    // fused edition: record stage (group, buffer) written by the gather warp
+  uint64_t rec_empty[TM_GROUPS * 2];   //                ... and read by all 8 epilogue warps of the group
   uint32_t tmem_base;
 };
 #define SM_TM_WF W_TC_BYTES
 #define SM_TM_GRP ((SM_TM_WF + F_TOTAL * 4 + 127) / 128 * 128)
 #define SM_TM_BAR (SM_TM_GRP + TM_GROUPS * (int)sizeof(TmGroup))
-#define SM_TM_TOTAL (SM_TM_BAR + 128)
+#define SM_TM_TOTAL (SM_TM_BAR + 256)
+#define SM_TM_REC SM_TM_TOTAL        // fused edition: [group][2][TM_REC_CH][BS] fp32 record stages
+#define SM_TMF_TOTAL (SM_TM_REC + TM_GROUPS * 2 * TM_REC_CH * BS * 4)
+static_assert(sizeof(TmBars) <= 256, "barrier block");
+static_assert(SM_TMF_TOTAL <= 227 * 1024, "shared memory of the fused colour kernel");
 
 // 16 values (consecutive k, k0 % 16 == 0) -> hi / lo words at TMEM columns k0/2 .. k0/2+7 of the A regions
 __device__ __forceinline__ void tm_store16(uint32_t t_hi, uint32_t t_lo, int k0, const float (&v)[16]) {
@@ -540,25 +548,34 @@ __device__ __forceinline__ void tm_issue(uint32_t tD, uint32_t a_hi, uint32_t a_
   tc::mma_commit(bar);
 }
 
-template <int V>
-__global__ void __launch_bounds__(TM_THREADS, 1)
+// FUSED: the records are not read from HBM but produced in the kernel: one extra warp per tile group projects the
+// group's next tile into the source views and gathers RGB + the feature pyramid (lookup_row, the body of
+// k_lookup_feature) into a double-buffered shared-memory stage while the group's 8 warps run the network on the
+// current tile.  Removes the 96 B / (point, view) HBM round trip and the separate gather kernel.
+template <int V, bool FUSED>
+__global__ void __launch_bounds__(FUSED ? TMF_THREADS : TM_THREADS, 1)
 k_blend_tm(const uint8_t* __restrict__ wtc, const float* __restrict__ wf32, float s_abs, const float* __restrict__ feat,
            const float* __restrict__ rdiff, const uint8_t* __restrict__ mask, int packed19,
            const int32_t* __restrict__ list, const int32_t* __restrict__ count, int64_t n, float* __restrict__ rgb_out,
-           uint8_t* __restrict__ views_out, int fast_i) {
+           uint8_t* __restrict__ views_out, int fast_i, const DevScene sc, const PointSource src) {
   const bool fast = fast_i != 0;
+  constexpr int NTHREADS = FUSED ? TMF_THREADS : TM_THREADS;
   extern __shared__ __align__(1024) uint8_t smem[];
   TmBars* bars = reinterpret_cast<TmBars*>(smem + SM_TM_BAR);
   const float* WF = reinterpret_cast<const float*>(smem + SM_TM_WF);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  for (int i = tid; i < W_TC_BYTES / 16; i += TM_THREADS)
+  for (int i = tid; i < W_TC_BYTES / 16; i += NTHREADS)
     reinterpret_cast<uint4*>(smem)[i] = reinterpret_cast<const uint4*>(wtc)[i];
-  for (int i = tid; i < F_TOTAL; i += TM_THREADS) reinterpret_cast<float*>(smem + SM_TM_WF)[i] = wf32[i];
+  for (int i = tid; i < F_TOTAL; i += NTHREADS) reinterpret_cast<float*>(smem + SM_TM_WF)[i] = wf32[i];
   if (warp == TM_GROUPS * TM_EPI_WARPS) tc::tmem_alloc<512>(&bars->tmem_base);
   if (tid == 0) {
     for (int g = 0; g < TM_GROUPS; ++g) {
       tc::mbar_init(&bars->a_ready[g], TM_EPI_WARPS);
       tc::mbar_init(&bars->d_full[g], 1);
+    }
+    for (int i = 0; i < TM_GROUPS * 2; ++i) {
+      tc::mbar_init(&bars->rec_full[i], 1);
+      tc::mbar_init(&bars->rec_empty[i], TM_EPI_WARPS);
     }
     tc::mbar_fence_init();
   }
@@ -599,7 +616,8 @@ k_blend_tm(const uint8_t* __restrict__ wtc, const float* __restrict__ wf32, floa
       ph++;
       tc::tc_fence_after();
     };
-    for (int64_t tile = (int64_t)blockIdx.x * TM_GROUPS + g; tile < n_tiles; tile += stride) {
+    uint32_t kt = 0;               // tiles this group has taken (record stage kt & 1, phase kt >> 1)
+    for (int64_t tile = (int64_t)blockIdx.x * TM_GROUPS + g; tile < n_tiles; tile += stride, ++kt) {
       // ---- record of my row: row r <-> (point tile*ppt + r / V, view r % V) ----
       const int64_t rec_i = tile * BT_ROWS + r;
       const bool ok = rec_i < n_total * V;
@@ -607,7 +625,12 @@ k_blend_tm(const uint8_t* __restrict__ wtc, const float* __restrict__ wf32, floa
       float4 rd = make_float4(0.f, 0.f, 0.f, 1.f);
 #pragma unroll
       for (int c = 0; c < FEAT_REC; ++c) rec[c] = 0.f;
-      if (ok) {
+      const int stage = g * 2 + (int)(kt & 1);
+      const float(*R)[BS] = reinterpret_cast<const float(*)[BS]>(smem + SM_TM_REC + stage * (TM_REC_CH * BS * 4));
+      if (FUSED) {       // the record comes from the group's gather warp through shared memory
+        tc::mbar_wait(&bars->rec_full[stage], (kt >> 1) & 1);
+        rd = make_float4(R[20][r], R[21][r], R[22][r], R[23][r]);
+      } else if (ok) {
         rd = reinterpret_cast<const float4*>(rdiff)[rec_i];
         if (packed19) {
           const float* f = feat + rec_i * 19;
@@ -637,16 +660,25 @@ k_blend_tm(const uint8_t* __restrict__ wtc, const float* __restrict__ wf32, floa
           float a = WF[F_DIR1_B + o];
 #pragma unroll
           for (int k = 0; k < 16; ++k) a = fmaf(w[k], h16[k], a);
-          G.X[o][r] = rec[o] + bt_elu(a);
+          G.X[o][r] = (FUSED ? R[o][r] : rec[o]) + bt_elu(a);
         }
       }
       if (half == 0) {
-        G.RGB[0][r] = rec[0]; G.RGB[1][r] = rec[1]; G.RGB[2][r] = rec[2];
+        if (FUSED) {
+          G.RGB[0][r] = R[0][r]; G.RGB[1][r] = R[1][r]; G.RGB[2][r] = R[2][r];
+          G.m[r] = R[19][r];
+        } else {
+          G.RGB[0][r] = rec[0]; G.RGB[1][r] = rec[1]; G.RGB[2][r] = rec[2];
+          G.m[r] = rec[19];
+        }
         G.RD[0][r] = rd.x; G.RD[1][r] = rd.y; G.RD[2][r] = rd.z; G.RD[3][r] = rd.w;
-        G.m[r] = rec[19];
         // pooling exponential, correctly rounded (see blend.cu / DESIGN.md §2)
         const float arg = __fmul_rn(s_abs, __fsub_rn(rd.w, 1.0f));
         G.e[r] = (float)exp((double)arg);
+      }
+      if (FUSED) {       // my reads of the record stage are done: hand it back to the gather warp
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&bars->rec_empty[stage]);
       }
       pair_sync();
       // ---- pooling weights of my point (blending_network.py:76-80) ----
@@ -856,7 +888,57 @@ k_blend_tm(const uint8_t* __restrict__ wtc, const float* __restrict__ wf32, floa
         }
       }
     }
-  } else {
+  } else if (FUSED && warp > TM_GROUPS * TM_EPI_WARPS) {
+    // =============================== projection-gather warps (one per group) ===============================
+    const int g = warp - TM_GROUPS * TM_EPI_WARPS - 1;
+    uint32_t kt = 0;
+    for (int64_t tile = (int64_t)blockIdx.x * TM_GROUPS + g; tile < n_tiles; tile += stride, ++kt) {
+      const int stage = g * 2 + (int)(kt & 1);
+      float(*R)[BS] = reinterpret_cast<float(*)[BS]>(smem + SM_TM_REC + stage * (TM_REC_CH * BS * 4));
+      tc::mbar_wait(&bars->rec_empty[stage], ((kt >> 1) & 1) ^ 1);
+      // phase 1: the sample positions of my 4 rows (the dependent loads list -> mid_z / ray of the rows overlap),
+      // parked in the ray_diff slots of the stage
+#pragma unroll
+      for (int j = 0; j < BT_ROWS / 32; ++j) {
+        const int row = j * 32 + lane;
+        const int64_t rec_i = tile * BT_ROWS + row;
+        float px = 0.f, py = 0.f, pz = 0.f;
+        if (rec_i < n_total * V) {
+          const int64_t i = rec_i / V;
+          if (src.mode == 0) {
+            px = src.pts[i * 3]; py = src.pts[i * 3 + 1]; pz = src.pts[i * 3 + 2];
+          } else {
+            const int64_t id = src.list ? (int64_t)src.list[i] : i;
+            const int64_t ray = id / src.S;
+            const float t = src.mid_z[id];
+            px = ray_at(src.rays_o[ray * 3], src.rays_d[ray * 3], t);
+            py = ray_at(src.rays_o[ray * 3 + 1], src.rays_d[ray * 3 + 1], t);
+            pz = ray_at(src.rays_o[ray * 3 + 2], src.rays_d[ray * 3 + 2], t);
+          }
+        }
+        R[20][row] = px; R[21][row] = py; R[22][row] = pz;
+      }
+      // phase 2: projection + gather, one row at a time (each lane only re-reads what it wrote)
+#pragma unroll 1
+      for (int j = 0; j < BT_ROWS / 32; ++j) {
+        const int row = j * 32 + lane;
+        const int64_t rec_i = tile * BT_ROWS + row;
+        float rec[FEAT_REC];
+        float4 rd = make_float4(0.f, 0.f, 0.f, 1.f);
+        if (rec_i < n_total * V) {
+          lookup_row(sc, R[20][row], R[21][row], R[22][row], (int)(rec_i % V), rec, rd);
+        } else {
+#pragma unroll
+          for (int c = 0; c < FEAT_REC; ++c) rec[c] = 0.f;
+        }
+#pragma unroll
+        for (int c = 0; c < FEAT_REC; ++c) R[c][row] = rec[c];
+        R[20][row] = rd.x; R[21][row] = rd.y; R[22][row] = rd.z; R[23][row] = rd.w;
+      }
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&bars->rec_full[stage]);
+    }
+  } else if (warp == TM_GROUPS * TM_EPI_WARPS) {
     // =============================== the MMA issuer ===============================
     if (tc::elect_one()) {
       const uint32_t w_a = tc::smem_u32(smem);
@@ -981,21 +1063,25 @@ int launch_blend_tc(const surf_net* n, const float* d_feat, const float* d_raydi
   const int ppt = BT_ROWS / V;
   const int64_t tiles = (n_pts + ppt - 1) / ppt;
   if (V == 2 || V == 4) {        // three tiles in flight per CTA, activations in TMEM, no block barriers
-    int rc = surf_ensure_dyn_smem((const void*)k_blend_tm<2>, SM_TM_TOTAL);
+    int rc = surf_ensure_dyn_smem((const void*)k_blend_tm<2, false>, SM_TM_TOTAL);
     if (rc) return rc;
-    rc = surf_ensure_dyn_smem((const void*)k_blend_tm<4>, SM_TM_TOTAL);
+    rc = surf_ensure_dyn_smem((const void*)k_blend_tm<4, false>, SM_TM_TOTAL);
     if (rc) return rc;
     const int64_t want = (tiles + TM_GROUPS - 1) / TM_GROUPS;
     const int grid = (int)(want < n->n_sm ? want : n->n_sm);
+    DevScene no_scene;
+    PointSource no_src;
+    memset(&no_scene, 0, sizeof(no_scene));
+    memset(&no_src, 0, sizeof(no_src));
     surf_time_begin(3, st);
     if (V == 2)
-      k_blend_tm<2><<<grid, TM_THREADS, SM_TM_TOTAL, st>>>(n->blend_tc_w, n->blend_tc_f, n->dev.blend_s, d_feat, d_raydiff,
-                                                          d_mask, packed19 ? 1 : 0, list, count, n_pts, d_rgb, d_views,
-                                                          fast ? 1 : 0);
+      k_blend_tm<2, false><<<grid, TM_THREADS, SM_TM_TOTAL, st>>>(n->blend_tc_w, n->blend_tc_f, n->dev.blend_s, d_feat,
+                                                                 d_raydiff, d_mask, packed19 ? 1 : 0, list, count, n_pts,
+                                                                 d_rgb, d_views, fast ? 1 : 0, no_scene, no_src);
     else
-      k_blend_tm<4><<<grid, TM_THREADS, SM_TM_TOTAL, st>>>(n->blend_tc_w, n->blend_tc_f, n->dev.blend_s, d_feat, d_raydiff,
-                                                          d_mask, packed19 ? 1 : 0, list, count, n_pts, d_rgb, d_views,
-                                                          fast ? 1 : 0);
+      k_blend_tm<4, false><<<grid, TM_THREADS, SM_TM_TOTAL, st>>>(n->blend_tc_w, n->blend_tc_f, n->dev.blend_s, d_feat,
+                                                                 d_raydiff, d_mask, packed19 ? 1 : 0, list, count, n_pts,
+                                                                 d_rgb, d_views, fast ? 1 : 0, no_scene, no_src);
     surf_time_end(3, st);
     SURF_LAUNCH_CHECK();
     return 0;
@@ -1014,6 +1100,38 @@ int launch_blend_tc(const surf_net* n, const float* d_feat, const float* d_raydi
     default: BT_LAUNCH(0); break;
   }
 #undef BT_LAUNCH
+  surf_time_end(3, st);
+  SURF_LAUNCH_CHECK();
+  return 0;
+}
+
+// projection gather + blending network in one kernel (render path, V in {2, 4}, tensor-core modes)
+bool color_fused_supported(const surf_scene* s, const surf_net* n, int mode) {
+  return mode != SURF_MLP_FFMA && n->blend_tc_w != nullptr && (s->dev.V == 2 || s->dev.V == 4);
+}
+
+int launch_color_fused(const surf_scene* s, const surf_net* n, const PointSource& src, float* d_rgb, uint8_t* d_views,
+                       bool fast, cudaStream_t st) {
+  SURF_CHECK_ARG(s->dev.img0, "scene has no images / feature maps");
+  if (src.n <= 0) return 0;
+  const int V = s->dev.V;
+  int rc = surf_ensure_dyn_smem((const void*)k_blend_tm<2, true>, SM_TMF_TOTAL);
+  if (rc) return rc;
+  rc = surf_ensure_dyn_smem((const void*)k_blend_tm<4, true>, SM_TMF_TOTAL);
+  if (rc) return rc;
+  const int ppt = BT_ROWS / V;
+  const int64_t tiles = (src.n + ppt - 1) / ppt;
+  const int64_t want = (tiles + TM_GROUPS - 1) / TM_GROUPS;
+  const int grid = (int)(want < n->n_sm ? want : n->n_sm);
+  surf_time_begin(3, st);
+  if (V == 2)
+    k_blend_tm<2, true><<<grid, TMF_THREADS, SM_TMF_TOTAL, st>>>(n->blend_tc_w, n->blend_tc_f, n->dev.blend_s, nullptr,
+                                                                nullptr, nullptr, 0, src.list, src.count, src.n, d_rgb,
+                                                                d_views, fast ? 1 : 0, s->dev, src);
+  else
+    k_blend_tm<4, true><<<grid, TMF_THREADS, SM_TMF_TOTAL, st>>>(n->blend_tc_w, n->blend_tc_f, n->dev.blend_s, nullptr,
+                                                                nullptr, nullptr, 0, src.list, src.count, src.n, d_rgb,
+                                                                d_views, fast ? 1 : 0, s->dev, src);
   surf_time_end(3, st);
   SURF_LAUNCH_CHECK();
   return 0;

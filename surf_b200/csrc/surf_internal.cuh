@@ -316,8 +316,11 @@ int launch_sdf_tc2(const surf_scene* s, const surf_net* n, const PointSource& sr
 int launch_blend_tc(const surf_net* n, const float* d_feat, const float* d_raydiff, const uint8_t* d_mask, int V,
                     bool packed19, const int32_t* list, const int32_t* count, int64_t n_pts, float* d_rgb,
                     uint8_t* d_views, bool fast, cudaStream_t st);
+bool color_fused_supported(const surf_scene* s, const surf_net* n, int mode);
+int launch_color_fused(const surf_scene* s, const surf_net* n, const PointSource& src, float* d_rgb, uint8_t* d_views,
+                       bool fast, cudaStream_t st);
 int launch_lookup_feature(const surf_scene* s, const PointSource& src, float* d_feat, float* d_raydiff,
-                          uint8_t* d_mask, bool packed19, cudaStream_t st);
+                          uint8_t* d_mask, bool packed19, cudaStream_t st, bool small_blocks = false);
 int launch_blend(const surf_scene* s_or_null, const surf_net* n, const float* d_feat, const float* d_raydiff,
                  const uint8_t* d_mask_or_null, int V, bool packed19, const int32_t* list, const int32_t* count,
                  int64_t n_pts, float* d_rgb, uint8_t* d_views, int mode, cudaStream_t st);

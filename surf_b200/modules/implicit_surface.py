@@ -119,6 +119,7 @@ class ImplicitSurface(nn.Module):
         if self.mlp_mode not in _lib.MLP_MODES:
             raise ValueError("mlp_mode must be one of %s" % (_lib.MLP_MODES,))
         cfg.mlp_mode = int(self.mlp_mode)
+        cfg.color_path = int(getattr(self, "color_path", _lib.COLOR_SERIAL))
         return cfg
 
     def _workspace(self, device, B, S, V):

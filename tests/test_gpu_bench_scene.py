@@ -292,3 +292,35 @@ def test_other_view_counts_vs_oracle(nv):
     r = compare_chunk(m, net, ps, sc_cpu, o, d, t, "nv=%d: " % nv, min_rows=0.8)
     print("nv=%d parity:" % nv, r)
     ps.destroy()
+
+
+# ------------------------------------------------------------------------------------------------
+# the three schedules of the colour path (surf_render_cfg.color_path): serial (default), gather kernel beside the SDF
+# kernel on a side stream, and gather fused into the blending kernel — same arithmetic per value, so bit-identical
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("nv,mode", [(5, _lib.MLP_TC), (3, _lib.MLP_TC), (5, _lib.MLP_TC_FAST), (4, _lib.MLP_TC),
+                                     (5, _lib.MLP_FFMA)])
+def test_colour_path_schedules_are_bit_identical(nv, mode):
+    sc = synthetic.make_scene(nv, 192, 256, 24, seed=50 + nv, device=DEV)
+    m = bench_net()
+    m.mlp_mode = mode
+    ps = m.prepare(sc.matching_volume, sc.volumes, sc.sparse_idxes, sc.mask_volumes, sc.imgs, sc.features, sc.intrs, sc.c2ws)
+    sc_cpu = sc.to("cpu")
+    del sc
+    n = 3000                                # ~400k points: many tiles per group, ragged last tile
+    o, d = synthetic.random_pixel_rays(sc_cpu, n, seed=9)
+    near, far = sc_cpu.near.expand(n, 1).to(DEV), sc_cpu.far.expand(n, 1).to(DEV)
+    t = torch.rand(n, 4, generator=torch.Generator().manual_seed(8))
+    pr = torch.rand(1024, 3, generator=torch.Generator().manual_seed(3)) * 2 - 1
+    outs = []
+    for path in (_lib.COLOR_SERIAL, _lib.COLOR_OVERLAP, _lib.COLOR_FUSED, _lib.COLOR_OVERLAP):
+        m.color_path = path
+        outs.append(m.render(o.to(DEV), d.to(DEV), near, far, ps, None, None, None, None, None, None, None, None, 1.0,
+                             None, t_rand=t, pts_random=pr, return_stages=True))
+    m.color_path = _lib.COLOR_SERIAL
+    a = outs[0]
+    assert int(a["_point_views"].ne(0).sum()) > 10000, "the scene should project into the source views"
+    for i, b in enumerate(outs[1:]):
+        for k in ("_point_color", "_point_views", "color_fine", "weights", "gradients", "sdf_depth"):
+            assert torch.equal(a[k], b[k]), "colour path %d differs from serial in %s (V=%d, mode %d)" % (i, k, nv - 1, mode)
+    ps.destroy()

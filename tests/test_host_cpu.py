@@ -83,7 +83,7 @@ def test_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(_lib.LIB_PATH)
     for name in declared:
         assert hasattr(lib, name), name
-    assert _lib.load().surf_version() == _lib.ABI_VERSION == 3
+    assert _lib.load().surf_version() == _lib.ABI_VERSION == 4
 
 
 def test_struct_sizes_match_header():
