@@ -7,6 +7,8 @@ the SDF grid, and one all-gather assembles the image / grid.  Works with any tor
 (NCCL on GPUs, gloo in the CPU tests)."""
 from __future__ import annotations
 
+import queue
+import threading
 from typing import Dict, List, Tuple
 
 import torch
@@ -113,16 +115,91 @@ def gather_grid(local_u: torch.Tensor, resolution: int) -> torch.Tensor:
     return _all_gather_ragged(local_u.contiguous(), sizes)
 
 
-def render_image_sharded(module, scene, rays_o, rays_d, near, far, cos_anneal_ratio=1.0, chunk=256, t_rand=None):
+def render_image_sharded(module, scene, rays_o, rays_d, near, far, cos_anneal_ratio=1.0, chunk=256, t_rand=None,
+                         jitter=None):
     """validate()'s image pass split over the ranks of the default process group + all-gather.
-    Every rank draws the same host jitter stream (same seed) and uses its slice."""
+    Every rank draws the same host jitter stream (same seed) and uses its slice; `jitter`: a JitterPrefetcher of this
+    rank's shard that draws it a step ahead on a worker thread instead."""
     rank, world = dist.get_rank(), dist.get_world_size()
     n = rays_o.shape[0]
-    if t_rand is None and module.perturb > 0:
-        t_rand = module.draw_chunk_randoms(n, chunk)
     r0, r1 = shard_rays(n, rank, world, chunk)
+    if jitter is not None:
+        mine = jitter.next()
+    else:
+        if t_rand is None and module.perturb > 0:
+            t_rand = module.draw_chunk_randoms(n, chunk)
+        mine = None if t_rand is None else t_rand[r0:r1]
     if near.shape[0] != 1:
         near, far = near[r0:r1], far[r0:r1]
-    res = module.render_image(scene, rays_o[r0:r1], rays_d[r0:r1], near, far, cos_anneal_ratio, chunk,
-                              None if t_rand is None else t_rand[r0:r1])
+    res = module.render_image(scene, rays_o[r0:r1], rays_d[r0:r1], near, far, cos_anneal_ratio, chunk, mine)
     return gather_image(res, n, chunk)
+
+
+class JitterPrefetcher:
+    """The jitter tables of consecutive images for ONE rank's ray shard, drawn a step ahead on a worker thread.
+
+    The reference draws its jitter from torch's global CPU generator, sequentially over the image (quirk Q1): 4 x
+    rand([256,1]) + rand([1024,3]) per 256-ray chunk, 7.4 M draws (~20 ms of mt19937) per 576x800 image.  To render a
+    shard bit-identically to the single-GPU image a rank has to consume the draws of the chunks before its shard, draw
+    its own, and consume the rest so that the NEXT image starts at the right place of the stream.  Done inline that is
+    ~20 ms of host time per image on every rank — more than the 17 ms an 8-GPU image takes on the device.  Here a
+    worker thread does it for image k+1 while the GPU renders image k; `next()` hands out a pinned (r1-r0, n_stages)
+    table.  The worker is the only consumer of the global generator while the prefetcher is open (seed before creating
+    it; close() it before drawing anything else)."""
+
+    def __init__(self, module, n_rays: int, r0: int, r1: int, chunk: int = 256, depth: int = 2):
+        assert (r0 % chunk == 0 or r0 == n_rays) and (r1 % chunk == 0 or r1 == n_rays), "shard borders must sit on chunk boundaries"
+        self._m, self._n, self._r0, self._r1, self._chunk = module, int(n_rays), int(r0), int(r1), int(chunk)
+        self._q: "queue.Queue" = queue.Queue(maxsize=max(1, depth))
+        self._stop = threading.Event()
+        self._err = None
+        self._pin = torch.cuda.is_available()
+        self._t = threading.Thread(target=self._work, name="surf-jitter", daemon=True)
+        self._t.start()
+
+    def _draws(self, n_rays: int) -> int:          # draws the chunks of n_rays rays consume (draw_chunk_randoms)
+        n_st = len(self._m.n_samples)
+        full, rem = divmod(n_rays, self._chunk)
+        from .modules.implicit_surface import N_RANDOM_PTS
+        return full * (n_st * self._chunk + N_RANDOM_PTS * 3) + ((n_st * rem + N_RANDOM_PTS * 3) if rem else 0)
+
+    def _work(self):
+        try:
+            while not self._stop.is_set():
+                if self._r0:
+                    torch.rand(self._draws(self._r0))                      # the chunks before my shard
+                if self._r1 > self._r0:
+                    t = self._m.draw_chunk_randoms(self._r1 - self._r0, self._chunk)
+                else:
+                    t = torch.empty((0, len(self._m.n_samples)))
+                if self._n > self._r1:
+                    torch.rand(self._draws(self._n - self._r1))            # ... and after it
+                if self._pin:
+                    t = t.pin_memory()
+                while not self._stop.is_set():
+                    try:
+                        self._q.put(t, timeout=0.05)
+                        break
+                    except queue.Full:
+                        continue
+        except BaseException as e:      # surfaced by next()
+            self._err = e
+
+    def next(self) -> torch.Tensor:
+        while True:
+            if self._err is not None:
+                raise RuntimeError("jitter worker failed") from self._err
+            try:
+                return self._q.get(timeout=0.05)
+            except queue.Empty:
+                continue
+
+    def close(self):
+        self._stop.set()
+        self._t.join()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()

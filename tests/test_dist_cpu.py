@@ -67,3 +67,25 @@ def test_gather_image_and_grid_gloo_world2():
         results = dict(q.get(timeout=10) for _ in range(2))
         assert results == {0: True, 1: True}, (n_rays, res, results)
         port = _free_port()
+
+
+def test_jitter_prefetcher_reproduces_the_sequential_stream():
+    """Every rank's prefetched tables = the rows of the single-process stream over consecutive images (Q1), bit for
+    bit, including a ragged last chunk and a rank whose shard is empty."""
+    import torch
+    from surf_b200 import conf
+    from surf_b200.dist import JitterPrefetcher, shard_rays
+    from surf_b200.modules.implicit_surface import ImplicitSurface
+    m = ImplicitSurface(conf.default_implicit_surface_conf())
+    n, images = 256 * 9 + 77, 3
+    torch.manual_seed(99)
+    want = [m.draw_chunk_randoms(n) for _ in range(images)]
+    for world in (1, 3, 16):
+        for rank in range(world):
+            r0, r1 = shard_rays(n, rank, world)
+            torch.manual_seed(99)
+            with JitterPrefetcher(m, n, r0, r1) as pf:
+                for k in range(images):
+                    got = pf.next()
+                    assert got.shape == (r1 - r0, 4)
+                    assert torch.equal(got, want[k][r0:r1]), (world, rank, k)
