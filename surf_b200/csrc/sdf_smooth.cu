@@ -29,9 +29,11 @@ struct SmoothSmem {
   // GEMV operands k-major with the 16 points innermost (row stride SM_PS floats, 16-byte aligned): a thread reads its 8
   // points of one k as two 128-bit broadcast loads (a [point][k] layout costs 16 scalar broadcasts per k and made the
   // kernel shared-memory-bandwidth bound: 5.6 ms for 70 k points)
-  float A[SM_STRIDE][SM_PS], Ad[SM_STRIDE][SM_PS];
-  float Z[6][SM_NP][128], Zd[6][SM_NP][128];
-  float GA[SM_STRIDE][SM_PS], GAd[SM_STRIDE][SM_PS];
+  // (the reverse pass needs softplus'(z_l) and softplus''(z_l) zd_l of every layer: 96 KB per 16 points.  They go to
+  // a per-block L2-resident scratch, written and read by the same thread, so that three blocks fit on an SM)
+  float A[SM_STRIDE][SM_PS], Ad[SM_STRIDE][SM_PS];       // forward operands; the reverse pass reuses them as ga / gad
+#define GA A
+#define GAd Ad
   float D[128][SM_PS], Dd[128][SM_PS];
   float PE[SM_NP][28], PEd[SM_NP][28], FT[SM_NP][28], FTd[SM_NP][28];
   float gpe[SM_NP][28], gdpe[SM_NP][28], gft[SM_NP][28], gdft[SM_NP][28];
@@ -120,13 +122,18 @@ __device__ __forceinline__ void sm_softplus(float z, float& h, float& d1, float&
   d2 = 100.0f * e * r * r;
 }
 
-__global__ void __launch_bounds__(SM_THREADS)
+#define SM_BLOCKS_PER_SM 3
+#define SM_SCRATCH_FLOAT2 (6 * SM_NP * 128)     // per block: (softplus', softplus'' zd) per (layer, point, neuron)
+
+__global__ void __launch_bounds__(SM_THREADS, SM_BLOCKS_PER_SM)
 k_sdf_smooth(const DevScene sc, const DevNet net, const float* __restrict__ wk, const int* __restrict__ wk_off,
              const float* __restrict__ wr, const int* __restrict__ wr_off, const float* __restrict__ pts,
-             const uint8_t* __restrict__ flags, int64_t n, float* __restrict__ grad_out, float* __restrict__ smooth_out) {
+             const uint8_t* __restrict__ flags, int64_t n, float* __restrict__ grad_out, float* __restrict__ smooth_out,
+             float2* __restrict__ scratch_all) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   SmoothSmem& S = *reinterpret_cast<SmoothSmem*>(smem_raw);
   const int tid = threadIdx.x;
+  float2* scratch = scratch_all + (size_t)blockIdx.x * SM_SCRATCH_FLOAT2;
   const int nid = tid & 127, pb = (tid >> 7) * SM_PH;     // my neuron / column, my first point
   const int pe_dim = net.pe_dim;       // 27
   for (int64_t base = (int64_t)blockIdx.x * SM_NP; base < n; base += (int64_t)gridDim.x * SM_NP) {
@@ -206,23 +213,22 @@ k_sdf_smooth(const DevScene sc, const DevNet net, const float* __restrict__ wk, 
         }
         const float b = W[(size_t)in_dim * SM_STRIDE + nid];
 #pragma unroll
-        for (int p = 0; p < SM_PH; ++p) { S.Z[l][pb + p][nid] = acc[p] + b; S.Zd[l][pb + p][nid] = accd[p]; }
-      } else {
-#pragma unroll
-        for (int p = 0; p < SM_PH; ++p) { S.Z[l][pb + p][nid] = 0.f; S.Zd[l][pb + p][nid] = 0.f; }
+        for (int p = 0; p < SM_PH; ++p) acc[p] += b;
       }
-      __syncthreads();
-      // next input [h | PE at the skip layer | features] and its tangent
-      for (int p = pb; p < pb + SM_PH; ++p) {
+      __syncthreads();          // every thread is done reading A / Ad of this layer
+      // next input [h | PE at the skip layer | features] and its tangent; the derivatives the reverse pass needs
+#pragma unroll
+      for (int p = 0; p < SM_PH; ++p) {
         float h = 0.f, hd = 0.f;
         if (nid < od) {
           float d1, d2;
-          sm_softplus(S.Z[l][p][nid], h, d1, d2);
-          hd = d1 * S.Zd[l][p][nid];
+          sm_softplus(acc[p], h, d1, d2);
+          hd = d1 * accd[p];
+          scratch[(size_t)(l * SM_NP + pb + p) * 128 + nid] = make_float2(d1, d2 * accd[p]);
         } else if (l + 1 == net.skip_layer && nid < od + pe_dim) {
-          h = S.PE[p][nid - od]; hd = S.PEd[p][nid - od];
+          h = S.PE[pb + p][nid - od]; hd = S.PEd[pb + p][nid - od];
         }
-        S.A[nid][p] = h; S.Ad[nid][p] = hd;
+        S.A[nid][pb + p] = h; S.Ad[nid][pb + p] = hd;
       }
       for (int i = tid; i < SM_NP * 28; i += SM_THREADS) {
         S.A[128 + i % 28][i / 28] = S.FT[i / 28][i % 28];
@@ -232,72 +238,100 @@ k_sdf_smooth(const DevScene sc, const DevNet net, const float* __restrict__ wk, 
       __syncthreads();
     }
     // ---- reverse with tangent: ga_6 = row 0 of lin6 / scale, gad_6 = 0 ----
+    // Work split of one reverse layer (156 input columns, od rows): thread nid owns hidden column nid over all rows; the
+    // 28 feature columns (128 + jq) are split by ROW QUARTER oq = nid >> 5 and their partial sums stay in registers
+    // across the layers (g_feat is the sum over the layers anyway) — a "column 128 + nid for nid < 28" split keeps one
+    // warp busy twice as long as the other three and was 17 % of the kernel's stall samples at the layer barrier.
+    // lin0 (27 PE columns) is split over the row quarters the same way.
+    const int jq = nid & 31, oq = nid >> 5;
+    float gf[SM_PH], gfd[SM_PH];
+#pragma unroll
+    for (int p = 0; p < SM_PH; ++p) { gf[p] = 0.f; gfd[p] = 0.f; }
     {
       const float* W6 = wr + wr_off[6];
-      for (int k = nid; k < SM_STRIDE; k += 128) {
-        const float w = k < 156 ? W6[k] * net.inv_scale : 0.f;
+      const float w = W6[nid] * net.inv_scale;
 #pragma unroll
-        for (int p = 0; p < SM_PH; ++p) { S.GA[k][pb + p] = w; S.GAd[k][pb + p] = 0.f; }
-      }
+      for (int p = 0; p < SM_PH; ++p) { S.GA[nid][pb + p] = w; S.GAd[nid][pb + p] = 0.f; }
     }
     __syncthreads();
     for (int l = 5; l >= 0; --l) {
       const int od = net.out_dim[l];
-      // feature columns of ga_{l+1}, PE columns of the skip layer's input
-      for (int i = tid; i < SM_NP * 28; i += SM_THREADS) {
-        S.gft[i / 28][i % 28] += S.GA[128 + i % 28][i / 28];
-        S.gdft[i / 28][i % 28] += S.GAd[128 + i % 28][i / 28];
-      }
+      // PE columns of the skip layer's input
       if (l + 1 == net.skip_layer)
         for (int i = tid; i < SM_NP * pe_dim; i += SM_THREADS) {
           S.gpe[i / pe_dim][i % pe_dim] += S.GA[od + i % pe_dim][i / pe_dim];
           S.gdpe[i / pe_dim][i % pe_dim] += S.GAd[od + i % pe_dim][i / pe_dim];
         }
       // delta_l and its tangent
-      for (int p = pb; p < pb + SM_PH; ++p) {
+#pragma unroll
+      for (int p = 0; p < SM_PH; ++p) {
         float dl = 0.f, dd = 0.f;
         if (nid < od) {
-          float h, d1, d2;
-          sm_softplus(S.Z[l][p][nid], h, d1, d2);
-          dl = S.GA[nid][p] * d1;
-          dd = S.GAd[nid][p] * d1 + S.GA[nid][p] * d2 * S.Zd[l][p][nid];
+          const float2 d = scratch[(size_t)(l * SM_NP + pb + p) * 128 + nid];     // (s'(z_l), s''(z_l) zd_l)
+          const float ga = S.GA[nid][pb + p];
+          dl = ga * d.x;
+          dd = fmaf(S.GAd[nid][pb + p], d.x, ga * d.y);
         }
-        S.D[nid][p] = dl; S.Dd[nid][p] = dd;
+        S.D[nid][pb + p] = dl; S.Dd[nid][pb + p] = dd;
       }
       __syncthreads();
-      const int I = (l == 0) ? pe_dim : 156;
       const float* W = wr + wr_off[l];
-      for (int k = nid; k < SM_STRIDE; k += 128) {
+      // sum over rows [o_lo, o_hi) of W[o][col] * (D[o], Dd[o]) for my 8 points, eight weight loads in flight
+      auto column = [&](int col, int o_lo, int o_hi, float (&ga)[SM_PH], float (&gad)[SM_PH]) {
+        for (int o0 = o_lo; o0 < o_hi; o0 += 8) {
+          float w8[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) w8[j] = (o0 + j < o_hi) ? __ldg(W + (size_t)(o0 + j) * SM_STRIDE + col) : 0.f;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int o = (o0 + j < o_hi) ? o0 + j : o_lo;
+            const float w = w8[j];
+            const float4 a0 = *reinterpret_cast<const float4*>(&S.D[o][pb]), a1 = *reinterpret_cast<const float4*>(&S.D[o][pb + 4]);
+            const float4 d0 = *reinterpret_cast<const float4*>(&S.Dd[o][pb]), d1 = *reinterpret_cast<const float4*>(&S.Dd[o][pb + 4]);
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float dv[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+            for (int p = 0; p < SM_PH; ++p) { ga[p] = fmaf(av[p], w, ga[p]); gad[p] = fmaf(dv[p], w, gad[p]); }
+          }
+        }
+      };
+      const int q_lo = oq * 32 < od ? oq * 32 : od, q_hi = oq * 32 + 32 < od ? oq * 32 + 32 : od;
+      if (l > 0) {
         float ga[SM_PH], gad[SM_PH];
 #pragma unroll
         for (int p = 0; p < SM_PH; ++p) { ga[p] = 0.f; gad[p] = 0.f; }
-        if (k < I) {
-          for (int o0 = 0; o0 < od; o0 += 8) {
-            float w8[8];
+        column(nid, 0, od, ga, gad);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) w8[j] = (o0 + j < od) ? __ldg(W + (size_t)(o0 + j) * SM_STRIDE + k) : 0.f;
+        for (int p = 0; p < SM_PH; ++p) { S.GA[nid][pb + p] = ga[p]; S.GAd[nid][pb + p] = gad[p]; }
+        if (jq < 28) column(128 + jq, q_lo, q_hi, gf, gfd);
+      } else {
+        // lin0: partial sums of PE column jq over my row quarter -> GA rows oq * 32 + jq, reduced below
+        float ga[SM_PH], gad[SM_PH];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const int o = (o0 + j < od) ? o0 + j : 0;
-              const float w = w8[j];
-              const float4 a0 = *reinterpret_cast<const float4*>(&S.D[o][pb]), a1 = *reinterpret_cast<const float4*>(&S.D[o][pb + 4]);
-              const float4 d0 = *reinterpret_cast<const float4*>(&S.Dd[o][pb]), d1 = *reinterpret_cast<const float4*>(&S.Dd[o][pb + 4]);
-              const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-              const float dv[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+        for (int p = 0; p < SM_PH; ++p) { ga[p] = 0.f; gad[p] = 0.f; }
+        if (jq < pe_dim) column(jq, q_lo, q_hi, ga, gad);
 #pragma unroll
-              for (int p = 0; p < SM_PH; ++p) { ga[p] = fmaf(av[p], w, ga[p]); gad[p] = fmaf(dv[p], w, gad[p]); }
-            }
-          }
-        }
-#pragma unroll
-        for (int p = 0; p < SM_PH; ++p) { S.GA[k][pb + p] = ga[p]; S.GAd[k][pb + p] = gad[p]; }
+        for (int p = 0; p < SM_PH; ++p) { S.GA[nid][pb + p] = ga[p]; S.GAd[nid][pb + p] = gad[p]; }
       }
       __syncthreads();
     }
-    // lin0's input is the positional encoding
-    for (int i = tid; i < SM_NP * pe_dim; i += SM_THREADS) {
-      S.gpe[i / pe_dim][i % pe_dim] += S.GA[i % pe_dim][i / pe_dim];
-      S.gdpe[i / pe_dim][i % pe_dim] += S.GAd[i % pe_dim][i / pe_dim];
+    // the feature-column partial sums of the four row quarters (D / Dd are free now)
+#pragma unroll
+    for (int p = 0; p < SM_PH; ++p) { S.D[nid][pb + p] = gf[p]; S.Dd[nid][pb + p] = gfd[p]; }
+    __syncthreads();
+    {
+      const float* W6 = wr + wr_off[6];
+      for (int i = tid; i < SM_NP * 28; i += SM_THREADS) {
+        const int p = i / 28, j = i % 28;
+        S.gft[p][j] = W6[128 + j] * net.inv_scale + ((S.D[j][p] + S.D[32 + j][p]) + (S.D[64 + j][p] + S.D[96 + j][p]));
+        S.gdft[p][j] = (S.Dd[j][p] + S.Dd[32 + j][p]) + (S.Dd[64 + j][p] + S.Dd[96 + j][p]);
+      }
+      // lin0's input is the positional encoding
+      for (int i = tid; i < SM_NP * pe_dim; i += SM_THREADS) {
+        const int p = i / pe_dim, j = i % pe_dim;
+        S.gpe[p][j] += (S.GA[j][p] + S.GA[32 + j][p]) + (S.GA[64 + j][p] + S.GA[96 + j][p]);
+        S.gdpe[p][j] += (S.GAd[j][p] + S.GAd[32 + j][p]) + (S.GAd[64 + j][p] + S.GAd[96 + j][p]);
+      }
     }
     __syncthreads();
     // ---- d/dx: feature part per (point, level), PE part per point ----
@@ -386,9 +420,15 @@ extern "C" int surf_sdf_smooth(const surf_scene* s, const surf_net* n, const flo
   int rc = surf_ensure_dyn_smem((const void*)k_sdf_smooth, (int)sizeof(SmoothSmem));
   if (rc) return rc;
   const int64_t blocks = (n_pts + SM_NP - 1) / SM_NP;
-  const int64_t cap = (int64_t)surf_num_sms() * 2;
+  int64_t cap = (int64_t)n->n_sm * SM_BLOCKS_PER_SM;
+  // the per-block derivative scratch lives in the network's scratch buffer (shared with the FFMA reverse pass: calls
+  // on one network handle are stream-ordered)
+  const int64_t fit = (int64_t)(n->scratch_bytes / (SM_SCRATCH_FLOAT2 * sizeof(float2)));
+  if (cap > fit) cap = fit;
+  SURF_CHECK_ARG(cap >= 1 && n->scratch, "network without scratch buffer");
   k_sdf_smooth<<<(int)(blocks < cap ? blocks : cap), SM_THREADS, sizeof(SmoothSmem), (cudaStream_t)stream>>>(
-      s->dev, n->dev, n->w_full, n->w_full_off, n->w_rows, n->w_rows_off, d_pts, d_flags, n_pts, d_grad, d_smooth);
+      s->dev, n->dev, n->w_full, n->w_full_off, n->w_rows, n->w_rows_off, d_pts, d_flags, n_pts, d_grad, d_smooth,
+      reinterpret_cast<float2*>(n->scratch));
   SURF_LAUNCH_CHECK();
   return 0;
 }
