@@ -221,11 +221,12 @@ int surf_sdf_full(const surf_scene* s, const surf_net* n, const float* d_pts, in
                   int32_t d_out_dim, void* stream);
 
 /* SDFNetworkSparse.gradient's second return value (sdf_network.py:143-150): smooth = d/dx sum_j (d sdf / d x_j) =
- * Hessian . (1,1,1), analytically (forward-mode tangent through the reverse pass), plain fp32 kernel — training only
- * (smooth_error, implicit_surface.py:172).  d_flags (nullable): per-point byte, bit 1 = evaluate, else write zeros
+ * Hessian . (1,1,1), analytically (forward-mode tangent through the reverse pass) — training only (smooth_error,
+ * implicit_surface.py:172).  mlp_mode: SURF_MLP_FFMA = plain fp32 kernel; SURF_MLP_TC = tcgen05 kernel, primal and
+ * tangent stream as two M = 128 GEMMs per layer, fp16 hi/lo 3-MMA split (fp32-grade); SURF_MLP_TC_FAST = one MMA.  d_flags (nullable): per-point byte, bit 1 = evaluate, else write zeros
  * (the reference's masked-out default, :99).  d_grad (nullable): the first-order gradient from the same pass. */
 int surf_sdf_smooth(const surf_scene* s, const surf_net* n, const float* d_pts, int64_t n_pts, const uint8_t* d_flags,
-                    float* d_grad, float* d_smooth, void* stream);
+                    float* d_grad, float* d_smooth, int32_t mlp_mode, void* stream);
 
 /* extract_geometry's SDF query (implicit_surface.py:337-351): u[x,y,z] = -sdf(xs[x],ys[y],zs[z]) on the
  * tensor-product grid of the three coordinate tables (host torch.linspace, uploaded).  Dense (Q16).

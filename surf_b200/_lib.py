@@ -205,7 +205,7 @@ def _declare(lib):
     lib.surf_sdf_full.restype = C.c_int
     lib.surf_sdf_full.argtypes = [vp, vp, vp, i64, vp, i32, vp]
     lib.surf_sdf_smooth.restype = C.c_int
-    lib.surf_sdf_smooth.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp]
+    lib.surf_sdf_smooth.argtypes = [vp, vp, vp, i64, vp, vp, vp, i32, vp]
     lib.surf_sdf_grid.restype = C.c_int
     lib.surf_sdf_grid.argtypes = [vp, vp, vp, i32, vp, i32, vp, i32, vp, i32, f32, i32, vp]
     lib.surf_point_mask.restype = C.c_int

@@ -362,7 +362,7 @@ extern "C" int surf_point_flags(const surf_scene* s, const surf_render_cfg* cfg,
 // network handle
 // ---------------------------------------------------------------------------------------------
 static int net_alloc(surf_net* n, void** p, size_t bytes) {
-  if (n->n_owned >= 16) {
+  if (n->n_owned >= 24) {
     surf_set_error("net: too many allocations");
     return -2;
   }

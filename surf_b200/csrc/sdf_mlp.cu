@@ -532,6 +532,8 @@ int surf_build_smooth_weights(const std::vector<std::vector<float>>& W, const su
                               cudaStream_t st, int (*dev_alloc)(surf_net*, void**, size_t));
 int surf_build_tc_weights(const std::vector<std::vector<float>>& W, const surf_net_inputs* in, surf_net* net,
                           cudaStream_t st, int (*dev_alloc)(surf_net*, void**, size_t));
+int surf_build_smooth_tc_weights(const std::vector<std::vector<float>>& W, const surf_net_inputs* in, surf_net* net,
+                                 cudaStream_t st, int (*dev_alloc)(surf_net*, void**, size_t));
 
 int surf_build_sdf_weights(const surf_net_inputs* in, surf_net* net, cudaStream_t st,
                            int (*dev_alloc)(surf_net*, void**, size_t)) {
@@ -671,6 +673,8 @@ int surf_build_sdf_weights(const surf_net_inputs* in, surf_net* net, cudaStream_
   net->tc_ok = (in->multires == 4 && skip == 3) ? 1 : 0;
   if (net->tc_ok) {
     rc = surf_build_tc_weights(W, in, net, st, dev_alloc);
+    if (rc) return rc;
+    rc = surf_build_smooth_tc_weights(W, in, net, st, dev_alloc);
     if (rc) return rc;
   }
   net->dev.b6 = in->h_bias[6][0];

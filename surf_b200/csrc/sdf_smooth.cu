@@ -17,6 +17,7 @@
 // in shared memory, weights read from L2 (k-major for the forward, row-major for the reverse: both coalesced).
 #include <vector>
 
+#include "smooth_common.cuh"
 #include "surf_internal.cuh"
 
 #define SM_NP 16             // points per block iteration
@@ -40,77 +41,6 @@ struct SmoothSmem {
   float pt[SM_NP][3];
   float part[SM_NP][4][3];
 };
-
-// one level of the sparse trilinear fetch with its tangent along v = (1,1,1) (world = grid direction, all ones):
-// f7 = value, fd7 = J_feat v
-__device__ __forceinline__ void sparse_value_tangent(const DevScene& sc, int l, float px, float py, float pz, float* f7,
-                                                     float* fd7) {
-  const int N = sc.dim[l];
-  const float vs = sc.voxel[l];
-  const float cx = __fdiv_rn(__fadd_rn(pz, 1.0f), vs), cy = __fdiv_rn(__fadd_rn(py, 1.0f), vs), cz = __fdiv_rn(__fadd_rn(px, 1.0f), vs);
-  const float fx0 = floorf(cx), fy0 = floorf(cy), fz0 = floorf(cz);
-  const float wx1 = __fsub_rn(cx, fx0), wx0 = __fsub_rn(fx0 + 1.0f, cx);
-  const float wy1 = __fsub_rn(cy, fy0), wy0 = __fsub_rn(fy0 + 1.0f, cy);
-  const float wz1 = __fsub_rn(cz, fz0), wz0 = __fsub_rn(fz0 + 1.0f, cz);
-  const float hi = (float)(N - 1);
-  const int x0 = (int)fminf(fmaxf(fx0, 0.f), hi), x1 = (int)fminf(fmaxf(fx0 + 1.0f, 0.f), hi);
-  const int y0 = (int)fminf(fmaxf(fy0, 0.f), hi), y1 = (int)fminf(fmaxf(fy0 + 1.0f, 0.f), hi);
-  const int z0 = (int)fminf(fmaxf(fz0, 0.f), hi), z1 = (int)fminf(fmaxf(fz0 + 1.0f, 0.f), hi);
-  const float inv = 1.0f / vs;
-#pragma unroll
-  for (int c = 0; c < 7; ++c) { f7[c] = 0.f; fd7[c] = 0.f; }
-#pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    const int xi = (c & 1) ? x1 : x0, yi = (c & 2) ? y1 : y0, zi = (c & 4) ? z1 : z0;
-    const int32_t row = __ldg(sc.index[l] + ((size_t)zi * N + yi) * N + xi);
-    if (row < 0) continue;
-    const float4 a = __ldg(sc.vol8[l] + (size_t)row * 2), b = __ldg(sc.vol8[l] + (size_t)row * 2 + 1);
-    const float wx = (c & 1) ? wx1 : wx0, wy = (c & 2) ? wy1 : wy0, wz = (c & 4) ? wz1 : wz0;
-    const float sx = (c & 1) ? 1.f : -1.f, sy = (c & 2) ? 1.f : -1.f, sz = (c & 4) ? 1.f : -1.f;
-    const float w = wx * wy * wz;
-    const float wd = (sx * wy * wz + sy * wx * wz + sz * wx * wy) * inv;
-    const float v[7] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z};
-#pragma unroll
-    for (int k = 0; k < 7; ++k) { f7[k] += v[k] * w; fd7[k] += v[k] * wd; }
-  }
-}
-
-// reverse of one level: o3 = J_feat^T g (world xyz), od3 = J_feat^T gd + Jd_feat^T g (tangent along (1,1,1))
-__device__ __forceinline__ void sparse_back_tangent(const DevScene& sc, int l, float px, float py, float pz, const float* g,
-                                                    const float* gd, float* o3, float* od3) {
-  const int N = sc.dim[l];
-  const float vs = sc.voxel[l];
-  const float cx = __fdiv_rn(__fadd_rn(pz, 1.0f), vs), cy = __fdiv_rn(__fadd_rn(py, 1.0f), vs), cz = __fdiv_rn(__fadd_rn(px, 1.0f), vs);
-  const float fx0 = floorf(cx), fy0 = floorf(cy), fz0 = floorf(cz);
-  const float wx1 = __fsub_rn(cx, fx0), wx0 = __fsub_rn(fx0 + 1.0f, cx);
-  const float wy1 = __fsub_rn(cy, fy0), wy0 = __fsub_rn(fy0 + 1.0f, cy);
-  const float wz1 = __fsub_rn(cz, fz0), wz0 = __fsub_rn(fz0 + 1.0f, cz);
-  const float hi = (float)(N - 1);
-  const int x0 = (int)fminf(fmaxf(fx0, 0.f), hi), x1 = (int)fminf(fmaxf(fx0 + 1.0f, 0.f), hi);
-  const int y0 = (int)fminf(fmaxf(fy0, 0.f), hi), y1 = (int)fminf(fmaxf(fy0 + 1.0f, 0.f), hi);
-  const int z0 = (int)fminf(fmaxf(fz0, 0.f), hi), z1 = (int)fminf(fmaxf(fz0 + 1.0f, 0.f), hi);
-  float gx = 0.f, gy = 0.f, gz = 0.f, hx = 0.f, hy = 0.f, hz = 0.f;
-#pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    const int xi = (c & 1) ? x1 : x0, yi = (c & 2) ? y1 : y0, zi = (c & 4) ? z1 : z0;
-    const int32_t row = __ldg(sc.index[l] + ((size_t)zi * N + yi) * N + xi);
-    if (row < 0) continue;
-    const float4 a = __ldg(sc.vol8[l] + (size_t)row * 2), b = __ldg(sc.vol8[l] + (size_t)row * 2 + 1);
-    const float wx = (c & 1) ? wx1 : wx0, wy = (c & 2) ? wy1 : wy0, wz = (c & 4) ? wz1 : wz0;
-    const float sx = (c & 1) ? 1.f : -1.f, sy = (c & 2) ? 1.f : -1.f, sz = (c & 4) ? 1.f : -1.f;
-    const float s = a.x * g[0] + a.y * g[1] + a.z * g[2] + a.w * g[3] + b.x * g[4] + b.y * g[5] + b.z * g[6];
-    const float sd = a.x * gd[0] + a.y * gd[1] + a.z * gd[2] + a.w * gd[3] + b.x * gd[4] + b.y * gd[5] + b.z * gd[6];
-    gx += s * (sx * wy * wz); gy += s * (sy * wx * wz); gz += s * (sz * wx * wy);
-    // d/d eps of the first derivatives: J^T gd plus the mixed second derivatives (d^2/dxdy = sx sy wz, ...)
-    hx += sd * (sx * wy * wz); hy += sd * (sy * wx * wz); hz += sd * (sz * wx * wy);
-    hx += s * (sx * (sy * wz + sz * wy)); hy += s * (sy * (sx * wz + sz * wx)); hz += s * (sz * (sx * wy + sy * wx));
-  }
-  const float inv = 1.0f / vs;
-  o3[0] = gz * inv; o3[1] = gy * inv; o3[2] = gx * inv;          // world x <- grid z (projector.py:379)
-  // the mixed terms carry 1 / vs^2, the J^T gd terms 1 / vs: split them
-  // (recomputed below to keep the two scalings apart)
-  od3[0] = hz; od3[1] = hy; od3[2] = hx;
-}
 
 __device__ __forceinline__ void sm_softplus(float z, float& h, float& d1, float& d2) {
   // softplus(beta = 100): h, h' = sigmoid(100 z), h'' = 100 h' (1 - h')
@@ -412,9 +342,12 @@ int surf_build_smooth_weights(const std::vector<std::vector<float>>& W, const su
 }
 
 extern "C" int surf_sdf_smooth(const surf_scene* s, const surf_net* n, const float* d_pts, int64_t n_pts,
-                               const uint8_t* d_flags, float* d_grad, float* d_smooth, void* stream) {
+                               const uint8_t* d_flags, float* d_grad, float* d_smooth, int32_t mlp_mode, void* stream) {
   if (n_pts <= 0) return 0;
   SURF_CHECK_ARG(s && n && d_pts && d_smooth, "null pointer");
+  SURF_CHECK_ARG(mlp_mode == SURF_MLP_FFMA || mlp_mode == SURF_MLP_TC || mlp_mode == SURF_MLP_TC_FAST, "mlp_mode must be SURF_MLP_FFMA, SURF_MLP_TC or SURF_MLP_TC_FAST");
+  if (mlp_mode != SURF_MLP_FFMA && n->tc_ok)
+    return launch_sdf_smooth_tc(s, n, d_pts, n_pts, d_flags, d_grad, d_smooth, mlp_mode == SURF_MLP_TC_FAST, (cudaStream_t)stream);
   SURF_CHECK_ARG(n->w_rows && n->w_full, "network without second-order weights");
   SURF_CHECK_ARG(n->dev.pe_dim <= 28 && n->dev.out_dim[6] >= 1, "unsupported network shape");
   int rc = surf_ensure_dyn_smem((const void*)k_sdf_smooth, (int)sizeof(SmoothSmem));

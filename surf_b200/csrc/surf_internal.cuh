@@ -90,7 +90,7 @@ struct T1Stream {
 
 struct surf_net {
   DevNet dev;
-  void* owned[16];
+  void* owned[24];
   int n_owned;
   const uint8_t* tc_blob;           // tensor-core weight stream (fp16 hi/lo chunks, forward then reverse)
   T1Stream tc_stream;               // chunk table of tc_blob in the order sdf_tc2.cu consumes it
@@ -101,6 +101,8 @@ struct surf_net {
   const int* w_full_off;            // float offset of each layer in w_full
   const float* w_rows;              // row-major fp32 matrices (stride 160) for the reverse passes of k_sdf_smooth
   const int* w_rows_off;
+  const uint8_t* smooth_tc_w;       // sdf_smooth_tc.cu: fp16 hi/lo operands of all 12 steps, in stream order
+  float2* smooth_tc_scratch;        // ... and its per-CTA softplus-derivative scratch
   int tc_ok;                        // network shape supported by the tensor-core kernels
   float* scratch;                   // sigma' scratch of the FFMA backward pass (per-CTA private)
   size_t scratch_bytes;
@@ -316,6 +318,8 @@ int launch_sdf_tc2(const surf_scene* s, const surf_net* n, const PointSource& sr
 int launch_blend_tc(const surf_net* n, const float* d_feat, const float* d_raydiff, const uint8_t* d_mask, int V,
                     bool packed19, const int32_t* list, const int32_t* count, int64_t n_pts, float* d_rgb,
                     uint8_t* d_views, bool fast, cudaStream_t st);
+int launch_sdf_smooth_tc(const surf_scene* s, const surf_net* n, const float* d_pts, int64_t n_pts, const uint8_t* d_flags,
+                         float* d_grad, float* d_smooth, bool fast, cudaStream_t st);
 bool color_fused_supported(const surf_scene* s, const surf_net* n, int mode);
 int launch_color_fused(const surf_scene* s, const surf_net* n, const PointSource& src, float* d_rgb, uint8_t* d_views,
                        bool fast, cudaStream_t st);

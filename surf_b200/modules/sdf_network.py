@@ -133,17 +133,19 @@ class SDFNetworkSparse(nn.Module):
             return sdf, grad
         return grad, self.smooth(x, scene)
 
-    def smooth(self, x, volumes, indexes=None, flags=None, with_grad=False):
+    def smooth(self, x, volumes, indexes=None, flags=None, with_grad=False, mode=None):
         """Hessian(sdf) . (1,1,1) at x (n,3) -> (n,3).  ``flags`` (n,) uint8: bit 1 = evaluate, else 0 (the reference's
-        masked-out default, implicit_surface.py:99).  ``with_grad``: also the fp32 first-order gradient of the same pass."""
-        scene, net, _ = self._handles(volumes, indexes)
+        masked-out default, implicit_surface.py:99).  ``with_grad``: also the first-order gradient of the same pass.
+        ``mode``: kernel family (default: the module's ``mlp_mode``; MLP_FFMA = the plain fp32 kernel)."""
+        scene, net, owner_mode = self._handles(volumes, indexes)
         x = x.detach().to(torch.float32).contiguous()
         sm = torch.empty((x.shape[0], 3), dtype=torch.float32, device=x.device)
         gr = torch.empty((x.shape[0], 3), dtype=torch.float32, device=x.device) if with_grad else None
         with torch.cuda.device(x.device):
             _lib.check(_lib.load().surf_sdf_smooth(scene.handle, net, x.data_ptr(), x.shape[0],
                                                    flags.data_ptr() if flags is not None else None,
-                                                   gr.data_ptr() if gr is not None else None, sm.data_ptr(), _stream()),
+                                                   gr.data_ptr() if gr is not None else None, sm.data_ptr(),
+                                                   int(owner_mode if mode is None else mode), _stream()),
                        "sdf_smooth")
         return (gr, sm) if with_grad else sm
 

@@ -125,8 +125,9 @@ def test_warp_maps_follow_the_views():
     assert torch.equal(a["ref_gray_val"], b["ref_gray_val"])        # the reference view did not change
 
 
+@pytest.mark.parametrize("mode", [_lib.MLP_TC, _lib.MLP_FFMA])
 @pytest.mark.parametrize("name", ["render_v2_perturbed", "render_v2_init", "render_v4_perturbed"])
-def test_second_order_smooth_vs_reference(name):
+def test_second_order_smooth_vs_reference(name, mode):
     """SDFNetworkSparse.gradient's second return value (sdf_network.py:143-150, double autograd) by the analytic
     forward-over-reverse kernel, against the reference's own `smooth` at the reference's evaluated points, and
     smooth_error of render() against the golden."""
@@ -134,6 +135,7 @@ def test_second_order_smooth_vs_reference(name):
     sc = scene_from_recipe(g["recipe"])
     m = ImplicitSurface(conf.default_implicit_surface_conf())
     m.load_state_dict(g["sd"])
+    m.mlp_mode = mode          # MLP_TC: the tcgen05 forward-over-reverse kernel; MLP_FFMA: the plain fp32 one
     m = m.to(DEV)
     d = sc.to(DEV)
     ps = m.prepare(d.matching_volume, d.volumes, d.sparse_idxes, d.mask_volumes, d.imgs, d.features, d.intrs, d.c2ws)
@@ -171,3 +173,26 @@ def test_second_order_smooth_wild_points():
     wild = g["in"]["wild_pts"].to(DEV)
     sm = m.sdf_network.smooth(wild, ps)
     assert_close(sm, g["out"]["wild_smooth"], 2e-4, "smooth, out-of-range points and exact voxel centres")
+
+
+def test_second_order_tensor_core_kernel_vs_fp32_kernel():
+    """The tcgen05 edition against the plain fp32 kernel on 40 k points of the cfgD-shaped scene (many tiles per CTA,
+    ragged last tile, masked-out points, points outside the volumes)."""
+    from surf_b200 import synthetic
+    import bench
+    sc = synthetic.make_scene(5, 240, 320, 32, seed=12, device=DEV)
+    m = bench.build_net(DEV)
+    ps = m.prepare(sc.matching_volume, sc.volumes, sc.sparse_idxes, sc.mask_volumes, sc.imgs, sc.features, sc.intrs, sc.c2ws)
+    g = torch.Generator(device=DEV).manual_seed(5)
+    pts = (torch.rand(40000 + 77, 3, device=DEV, generator=g) * 2.4 - 1.2)
+    fl = (torch.rand(pts.shape[0], device=DEV, generator=g) < 0.8).to(torch.uint8) * 2
+    g_tc, s_tc = m.sdf_network.smooth(pts, ps, flags=fl, with_grad=True, mode=_lib.MLP_TC)
+    g_32, s_32 = m.sdf_network.smooth(pts, ps, flags=fl, with_grad=True, mode=_lib.MLP_FFMA)
+    assert bool(torch.isfinite(s_tc).all()) and float(s_32.abs().max()) > 0
+    assert bool((s_tc[fl == 0] == 0).all()) and bool((g_tc[fl == 0] == 0).all())
+    assert_close(g_tc, g_32, 1e-4, "first-order gradient, tensor-core vs fp32 second-order kernel")
+    assert_close(s_tc, s_32, 2e-4, "smooth, tensor-core vs fp32 second-order kernel")
+    # bitwise reproducible and independent of the tile a point lands in
+    assert torch.equal(m.sdf_network.smooth(pts, ps, flags=fl, mode=_lib.MLP_TC), s_tc)
+    assert torch.equal(m.sdf_network.smooth(pts[1000:3001], ps, flags=fl[1000:3001], mode=_lib.MLP_TC), s_tc[1000:3001])
+    ps.destroy()

@@ -15,7 +15,8 @@ def t(fn, n=5):
     for _ in range(n): fn()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n
-print("smooth kernel, 69632 points: %.3f ms" % t(lambda: m.sdf_network.smooth(pts, ps, flags=fl)))
+print("smooth kernel (tcgen05), 69632 points: %.3f ms" % t(lambda: m.sdf_network.smooth(pts, ps, flags=fl, mode=1)))
+print("smooth kernel (fp32 FFMA), 69632 points: %.3f ms" % t(lambda: m.sdf_network.smooth(pts, ps, flags=fl, mode=0)))
 print("gradient (tcgen05), 69632 points: %.3f ms" % t(lambda: m.sdf_network.gradient(pts, ps, with_sdf=True)))
 o, d = synthetic.random_pixel_rays(sc, 512, seed=1)
 o, d = o.cuda(), d.cuda()
