@@ -267,7 +267,7 @@ k_sdf_smooth_tc(const DevScene sc, const DevNet net, const uint8_t* __restrict__
       for (int u = 0; u < 2; ++u) {
         const int lv = hf * 2 + u;
         float f7[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, fd7[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        if (inb && lv < sc.n_levels) sparse_value_tangent(sc, lv, px, py, pz, f7, fd7);
+        if (inb && lv < sc.n_levels) sparse_value_tangent_batched(sc, lv, px, py, pz, f7, fd7);
 #pragma unroll
         for (int c = 0; c < 7; ++c) {
           st_put_half(smem + ST_SM_AFP, 8192, r, lv * 7 + c, f7[c]);
@@ -329,11 +329,24 @@ k_sdf_smooth_tc(const DevScene sc, const DevNet net, const uint8_t* __restrict__
       float g1[3] = {0.f, 0.f, 0.f}, s2[3] = {0.f, 0.f, 0.f};       // PE part of d/dx and of the second-order term
 #pragma unroll 1
       for (int l = 5; l >= 1; --l) {
-        wait_d();
         const bool pe_layer = (l == 3) && (hf == 1);
+        // (s', s'' zd) of layer l-1, one chunk of 16 columns ahead of its use: the first chunk is fetched before the
+        // accumulator wait, the loads never sit between a TMEM read and its use
+        const float2* sl = scratch + (size_t)((l - 1) * 128 + hf * 64) * 128 + r;
+        float2 dn[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) dn[j] = sl[(size_t)j * 128];
+        wait_d();
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           const int cb = hf * 64 + c * 16;
+          float2 dc[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) dc[j] = dn[j];
+          if (c < 3) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) dn[j] = sl[(size_t)((c + 1) * 16 + j) * 128];
+          }
           uint32_t ga[16], gad[16];
           tc::tmem_ld16(tl + ST_D0 + cb, ga);
           tc::tmem_ld16(tl + ST_D1 + cb, gad);
@@ -341,16 +354,14 @@ k_sdf_smooth_tc(const DevScene sc, const DevNet net, const uint8_t* __restrict__
           float a[16], b[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const int col = cb + j;
             const float g = __uint_as_float(ga[j]), gd = __uint_as_float(gad[j]);
             if (c >= 2 && 64 + c * 16 + j >= 101 && pe_layer) {       // gradient w.r.t. the PE part of the skip layer's input
               st_pe_accum(PE, r, 64 + c * 16 + j - 101, scale, g, gd, g1, s2);
               a[j] = 0.f;
               b[j] = 0.f;
             } else {
-              const float2 d = scratch[(size_t)((l - 1) * 128 + col) * 128 + r];    // (s', s'' zd) of layer l-1
-              a[j] = g * d.x;
-              b[j] = fmaf(gd, d.x, g * d.y);
+              a[j] = g * dc[j].x;
+              b[j] = fmaf(gd, dc[j].x, g * dc[j].y);
             }
           }
           st_store_tmem(t_hi, t_lo, cb, a);
@@ -384,15 +395,13 @@ k_sdf_smooth_tc(const DevScene sc, const DevNet net, const uint8_t* __restrict__
         }
 #pragma unroll
         for (int k = 0; k < 14; ++k) gf[k] = fmaf(net.w6[128 + hf * 14 + k], c6s, gf[k]);    // lin6 sees the features too
-        const float zero7[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
           const int lv = hf * 2 + u;
           if (inb && lv < sc.n_levels) {
-            float t3[3], od3[3], g3[3], om3[3];
-            // J^T gd (scaled 1/vs): a first-order pass with gd;  J^T g and the mixed terms (1/vs^2): a pass with g
-            sparse_back_tangent(sc, lv, px, py, pz, &gfd[u * 7], zero7, od3, t3);
-            sparse_back_tangent(sc, lv, px, py, pz, &gf[u * 7], zero7, g3, om3);
+            float g3[3], od3[3], om3[3];
+            // J^T g and J^T gd (scaled 1/vs), the mixed second derivatives contracted with g (1/vs^2)
+            sparse_back_fused(sc, lv, px, py, pz, &gf[u * 7], &gfd[u * 7], g3, od3, om3);
             const float inv = 1.0f / sc.voxel[lv];
 #pragma unroll
             for (int d = 0; d < 3; ++d) {
