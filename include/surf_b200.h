@@ -356,6 +356,37 @@ int surf_mc_emit(const float* d_u, int32_t nx, int32_t ny, int32_t nz, float thr
                  int32_t x_offset, double* d_vertices, int64_t n_vertices, int32_t* d_triangles, int64_t n_triangles,
                  void* stream);
 
+/* ---- mesh cleaning after extract_geometry (utils/clean_mesh.py:10-129, runner.py:233 `--clean_mesh`) ----
+ * Replaces the host pipeline skimage.binary_dilation -> torch projection -> trimesh/embree ray casting ->
+ * trimesh connected components.  All buffers are the caller's; h_* pointers are HOST arrays (row-major).
+ *   surf_mask_dilate              binary dilation of (n_views,h,w) byte masks with skimage's disk(radius), zero border
+ *                                 (:119-123); d_workspace: n_views*h*w int32
+ *   surf_mesh_vertex_visibility   d_count[i] = number of views in which vertex i projects inside the image and onto a set
+ *                                 pixel of the mask (bilinear tap, align_corners=True, zero padding) (:12-28);
+ *                                 h_w2c (n_views,3,4) = inverse(c2w)[:3], h_K (n_views,3,3)
+ *   surf_mesh_first_hits          one view: d_face_hit[f] = 1 for every face that is the first hit of a camera ray
+ *                                 through the (hs,ws) sample grid linspace(0,h-1,hs) x linspace(0,w-1,ws) whose
+ *                                 nearest-upsampled mask pixel is set (:41-78; the reference casts them with embree);
+ *                                 d_face_hit is OR-ed into (zero it before the first view).  d_stats (int32[2]):
+ *                                 [0] += masked rays without a hit, [1] = faces with a footprint above 4096 samples
+ *                                 (more than 65536 of them is an error the caller must check)
+ *   surf_mesh_components          d_label[f] = component id (smallest face index of the component) of the graph that
+ *                                 links two faces sharing an edge no third face shares (trimesh face_adjacency);
+ *                                 d_keep[f] = 1 when the component has at least min_len faces (:99-102) */
+int surf_mask_dilate(const uint8_t* d_masks, int32_t n_views, int32_t h, int32_t w, int32_t radius, int32_t* d_workspace,
+                     uint8_t* d_out, void* stream);
+int surf_mesh_vertex_visibility(const float* d_vertices, int64_t n_vertices, const float* h_w2c, const float* h_K,
+                                int32_t n_views, const uint8_t* d_masks, int32_t h, int32_t w, int32_t* d_count,
+                                void* stream);
+size_t surf_mesh_raster_workspace_bytes(int32_t hs, int32_t ws);
+int surf_mesh_first_hits(const float* d_vertices, const int32_t* d_faces, int64_t n_faces, const float* h_w2c,
+                         const float* h_c2w, const float* h_K, const uint8_t* d_mask, int32_t h, int32_t w, int32_t hs,
+                         int32_t ws, void* d_workspace, size_t workspace_bytes, uint8_t* d_face_hit, int32_t* d_stats,
+                         void* stream);
+size_t surf_mesh_components_workspace_bytes(int64_t n_faces);
+int surf_mesh_components(const int32_t* d_faces, int64_t n_faces, int32_t min_len, void* d_workspace,
+                         size_t workspace_bytes, int32_t* d_label, uint8_t* d_keep, void* stream);
+
 int surf_version(void);
 const char* surf_last_error(void);
 /* number of kernel launches issued by this library in this process (bench.py's gpu_launches) */

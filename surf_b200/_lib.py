@@ -33,6 +33,8 @@ EXPORTS = [
     "surf_net_create", "surf_net_destroy",
     "surf_render_workspace_bytes", "surf_sample_rays", "surf_render_core", "surf_render_rays",
     "surf_sdf_points", "surf_sdf_grid", "surf_sdf_full", "surf_sdf_smooth",
+    "surf_mask_dilate", "surf_mesh_vertex_visibility", "surf_mesh_raster_workspace_bytes", "surf_mesh_first_hits",
+    "surf_mesh_components_workspace_bytes", "surf_mesh_components",
     "surf_point_mask", "surf_lookup_sparse", "surf_lookup_feature", "surf_blend", "surf_point_flags",
     "surf_tc_selftest",
     "surf_mc_workspace_bytes", "surf_mc_count", "surf_mc_emit",
@@ -204,6 +206,18 @@ def _declare(lib):
     lib.surf_sdf_points.argtypes = [vp, vp, vp, i64, vp, vp, i32, vp]
     lib.surf_sdf_full.restype = C.c_int
     lib.surf_sdf_full.argtypes = [vp, vp, vp, i64, vp, i32, vp]
+    lib.surf_mask_dilate.restype = C.c_int
+    lib.surf_mask_dilate.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp]
+    lib.surf_mesh_vertex_visibility.restype = C.c_int
+    lib.surf_mesh_vertex_visibility.argtypes = [vp, i64, vp, vp, i32, vp, i32, i32, vp, vp]
+    lib.surf_mesh_raster_workspace_bytes.restype = C.c_size_t
+    lib.surf_mesh_raster_workspace_bytes.argtypes = [i32, i32]
+    lib.surf_mesh_first_hits.restype = C.c_int
+    lib.surf_mesh_first_hits.argtypes = [vp, vp, i64, vp, vp, vp, vp, i32, i32, i32, i32, vp, C.c_size_t, vp, vp, vp]
+    lib.surf_mesh_components_workspace_bytes.restype = C.c_size_t
+    lib.surf_mesh_components_workspace_bytes.argtypes = [i64]
+    lib.surf_mesh_components.restype = C.c_int
+    lib.surf_mesh_components.argtypes = [vp, i64, i32, vp, C.c_size_t, vp, vp, vp]
     lib.surf_sdf_smooth.restype = C.c_int
     lib.surf_sdf_smooth.argtypes = [vp, vp, vp, i64, vp, vp, vp, i32, vp]
     lib.surf_sdf_grid.restype = C.c_int

@@ -57,11 +57,13 @@ def export_mesh(vertices: np.ndarray, triangles: np.ndarray, scale_mat, path: st
 
 @torch.no_grad()
 def validate(model, val_loader: Iterable[Dict], base_exp_dir: str, epoch: int = 0, anneal_end: float = 0.0,
-             device="cuda:0", tag: str = "epoch", **val_kwargs) -> Dict[str, float]:
+             device="cuda:0", tag: str = "epoch", clean_mesh: bool = False, **val_kwargs) -> Dict[str, float]:
     """One validation pass: per item a rendered image, normal map, two depth maps (.png + .npy) and the mesh, exactly
     the files runner.py:243-262 writes; returns the averaged scalars of runner.py:264-286.  ``tag='step'`` gives the
     file names of the finetune validation block (runner.py:377-388).  ``val_kwargs`` are forwarded to
-    ``ImplicitSurface.validate`` through ``model.val_options`` when the model supports it (e.g. mesh_resolution)."""
+    ``ImplicitSurface.validate`` through ``model.val_options`` when the model supports it (e.g. mesh_resolution).
+    ``clean_mesh`` = the reference's ``--clean_mesh`` switch (runner.py:233-234): the mesh is cleaned against
+    ``inputs["masks"]`` on the GPU (surf_b200.clean_mesh) before it is transformed and written."""
     from PIL import Image
     model.eval()
     items = list(val_loader)
@@ -80,6 +82,11 @@ def validate(model, val_loader: Iterable[Dict], base_exp_dir: str, epoch: int = 
             for sub in ("meshes", "val_img", "val_normal", "val_sdf_depth", "val_render_depth"):
                 os.makedirs(os.path.join(base_exp_dir, sub), exist_ok=True)
             if "vertices" in outputs:
+                if clean_mesh:          # runner.py:233-234
+                    from .clean_mesh import clean_mesh as _clean
+                    outputs["vertices"], outputs["triangles"] = _clean(outputs["vertices"], outputs["triangles"],
+                                                                       inputs["masks"], inputs["intrs"], inputs["c2ws"],
+                                                                       device=device)
                 export_mesh(outputs["vertices"], outputs["triangles"], inputs.get("scale_mat", np.eye(4)),
                             os.path.join(base_exp_dir, "meshes", "%s%s.ply" % (scene, sfx)))
             Image.fromarray(outputs["img_fine"].astype(np.uint8)).save(os.path.join(base_exp_dir, "val_img", file_name + sfx + ".png"))

@@ -2,12 +2,12 @@
 """Secondary benchmark configurations of BASELINE.json (configs[3], configs[4]); bench.py measures the headline
 (configs[1]) and the 512^3 grid (configs[2]).  Prints one JSON line per configuration (rank 0).
 
-    python tools/bench_configs.py cfgD [--steps K]          # training-shape render, all training keys but smooth_error
+    python tools/bench_configs.py cfgD [--steps K]          # training-shape render, all 18 training keys
     python tools/bench_configs.py cfgE [--steps K]          # Tanks-and-Temples-shaped image, reduced-precision MLP mode
     torchrun --nproc-per-node N ... tools/bench_configs.py cfgD|cfgE
 
 cfgD: 4 x scene(5, 480, 640, base 64, seed 10+s), 512 random-pixel rays each, train-mode render()
-(17 of the reference's 18 keys incl. the third MLP pass and the 11x11 patch warps); N ranks: rank r <-> scene r // 2,
+(all 18 keys of the reference incl. the third MLP pass, the 11x11 patch warps and the second-order smooth_error); N ranks: rank r <-> scene r // 2,
 half r % 2 of its rays (scene-major, no collective).
 cfgE: scene(5, 1080, 1920, base 176 -> 1408^3 finest level, seed 20), n_samples = [64,32,16,16] (128 / ray), one image
 of 2 073 600 rays in the opt-in one-MMA mode (tolerance 1e-2), ray-sharded over the ranks + NCCL all-gather.
@@ -69,6 +69,14 @@ def main():
         for u_i, (s, h) in enumerate(units):
             if u_i % world == rank:
                 jobs.append((s, h * per_scene // 2, (h + 1) * per_scene // 2))
+        # a rank that holds both halves of a scene renders it in one call (the calls are launch-bound)
+        merged = []
+        for s, a, b in jobs:
+            if merged and merged[-1][0] == s and merged[-1][2] == a:
+                merged[-1] = (s, merged[-1][1], b)
+            else:
+                merged.append((s, a, b))
+        jobs = merged
         scenes = {}
         for s, a, b in jobs:
             if s not in scenes:
@@ -101,7 +109,7 @@ def main():
                                        "batch, volumes %d->%d, train-mode render() incl. patch warps" % (base, base * 8),
                            "parallelism": "scene-major: rank r <-> scene r // 2, half r % 2" if world > 1 else "1 GPU"},
                 "gpu_launches": int(launches), "output_keys": keys,
-                "missing_vs_reference": ["smooth_error (second-order autograd)", "autograd through the render"]}
+                "missing_vs_reference": ["autograd through the render (outputs are detached)"]}
     else:
         base = args.base or 176
         c = conf.default_implicit_surface_conf()
