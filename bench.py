@@ -54,6 +54,9 @@ def parse():
     ap.add_argument("--grid", type=int, default=GRID_RES, help="SDF grid resolution (0 = skip)")
     ap.add_argument("--cpu-rays", type=int, default=8192, help="rays per CPU-baseline sample / reference-arm step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--level0", default="frustum", choices=["frustum", "all"],
+                    help="coarsest voxel mask of the synthetic scene: SURVEY 8d's formula (default) or every voxel occupied "
+                         "(8d's voxel counts; a real scene with cameras all around)")
     ap.add_argument("--color-path", type=int, default=0, choices=[0, 1, 2],
                     help="A/B: 0 gather then blend (default), 1 gather beside the SDF kernel, 2 gather fused into the blend")
     ap.add_argument("--scaling", default="strong", choices=["weak", "strong"],
@@ -288,7 +291,8 @@ def config_dict(args, world, strong):
             "parallelism": ("1 GPU" if world == 1 else
                             ("one image, rays sharded x%d on 256-ray chunk boundaries + NCCL all-gather of tiles" % world
                              if strong else "%d independent images (one per rank), no collective" % world)),
-            "l2": "inputs larger than L2 (prepared scene > 2 GB, ~13 GB of per-step intermediates)"}
+            "l2": "inputs larger than L2 (prepared scene > 2 GB, ~13 GB of per-step intermediates)",
+            **({"level0": "all voxels of the coarsest level occupied"} if getattr(args, "level0", "frustum") == "all" else {})}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -302,7 +306,7 @@ def run_reference(args):
     from surf_b200 import synthetic
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     dev = "cuda" if torch.cuda.is_available() else "cpu"
-    sc = synthetic.make_scene(args.views, args.height, args.width, args.base, seed=1, device=dev)
+    sc = synthetic.make_scene(args.views, args.height, args.width, args.base, seed=1, device=dev, level0=args.level0)
     sc_cpu = sc.to("cpu")
     del sc
     m = build_net()
@@ -400,7 +404,7 @@ def run_gpu(args):
     # ---- scene + network (generated on the device; scene_prepare timed separately) ----------------
     # every rank holds the same scene (seed 1): strong scaling shards ONE image; the secondary weak measurement
     # renders the same image on every rank
-    sc = synthetic.make_scene(args.views, args.height, args.width, args.base, seed=1, device=dev)
+    sc = synthetic.make_scene(args.views, args.height, args.width, args.base, seed=1, device=dev, level0=args.level0)
     m = build_net(dev)
     m.mlp_mode = args.mlp_mode
     m.color_path = int(args.color_path)

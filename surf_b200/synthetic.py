@@ -137,8 +137,11 @@ def _shell_mask(n, parent, thresh, device, slab=64):
 
 
 def make_scene(nv=3, H=576, W=800, base=88, seed=1, device="cpu", n_levels=4, feat_ch=7,
-               range_ratios=RANGE_RATIOS) -> Scene:
-    """scene(nv, H, W, base, seed) of SURVEY.md §8d.  Deterministic for a given (args, device type)."""
+               range_ratios=RANGE_RATIOS, level0="frustum") -> Scene:
+    """scene(nv, H, W, base, seed) of SURVEY.md §8d.  Deterministic for a given (args, device type).
+    ``level0``: "frustum" = the coarsest mask is "voxel centre visible in >= 2 views" of THIS camera rig, as §8d's
+    formula says (0.16 M / 1.3 M / 4.9 M / 4.6 M voxels at base 88); "all" = every coarsest voxel occupied, what a real
+    scene with cameras all around gives and what §8d's voxel counts (0.68 M / 5.3 M / 8.6 M / 6.4 M) correspond to."""
     device = torch.device(device)
     g = torch.Generator(device=device)
     intrs, c2ws, near, far = make_cameras(nv, H, W, device)
@@ -148,7 +151,9 @@ def make_scene(nv=3, H=576, W=800, base=88, seed=1, device="cpu", n_levels=4, fe
     parent = None
     for l in range(n_levels):
         n = base * (2 ** l)
-        if l == 0:
+        if l == 0 and level0 == "all":
+            m = torch.ones((n, n, n), dtype=torch.bool, device=device)
+        elif l == 0:
             m = _frustum_mask(n, intrs, c2ws, H, W, device)
         else:
             m = _shell_mask(n, parent, base_range * range_ratios[l], device)
