@@ -216,12 +216,39 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
 }
 
 // ---- fp16 hi/lo split -------------------------------------------------------------------------------
-// x = hi + lo with hi = fp16(x), lo = fp16(x - hi): 22 significant bits through two fp16 MMAs
+// x - float(h) in ONE instruction (FHFMA: fp16 x fp16 + fp32 with the product term h * -1; exact, like the FADD of the
+// converted value it replaces); HI selects the upper half of the packed pair
+template <int HI>
+__device__ __forceinline__ float sub_half(float x, uint32_t packed) {
+  float d;
+  const unsigned short m1 = 0xBC00;      // -1.0 (fp16)
+  if (HI)
+    asm("{\n\t.reg .f16 lo, hi, m;\n\tmov.b32 {lo, hi}, %1;\n\tmov.b16 m, %3;\n\tfma.rn.f32.f16 %0, hi, m, %2;\n\t}"
+        : "=f"(d) : "r"(packed), "f"(x), "h"(m1));
+  else
+    asm("{\n\t.reg .f16 lo, hi, m;\n\tmov.b32 {lo, hi}, %1;\n\tmov.b16 m, %3;\n\tfma.rn.f32.f16 %0, lo, m, %2;\n\t}"
+        : "=f"(d) : "r"(packed), "f"(x), "h"(m1));
+  return d;
+}
+// float(h) + c in one instruction
+template <int HI>
+__device__ __forceinline__ float add_half(uint32_t packed, float c) {
+  float d;
+  const unsigned short p1 = 0x3C00;      // 1.0 (fp16)
+  if (HI)
+    asm("{\n\t.reg .f16 lo, hi, m;\n\tmov.b32 {lo, hi}, %1;\n\tmov.b16 m, %3;\n\tfma.rn.f32.f16 %0, hi, m, %2;\n\t}"
+        : "=f"(d) : "r"(packed), "f"(c), "h"(p1));
+  else
+    asm("{\n\t.reg .f16 lo, hi, m;\n\tmov.b32 {lo, hi}, %1;\n\tmov.b16 m, %3;\n\tfma.rn.f32.f16 %0, lo, m, %2;\n\t}"
+        : "=f"(d) : "r"(packed), "f"(c), "h"(p1));
+  return d;
+}
+// x = hi + lo with hi = fp16(x), lo = fp16(x - hi): 22 significant bits through two fp16 MMAs.  4 instructions per
+// pair (F2FP, 2 FHFMA, F2FP); the plain formulation (unpack hi to fp32, subtract) takes 6
 __device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
   const __half2 h = __floats2half2_rn(x0, x1);
-  const float2 b = __half22float2(h);
-  const __half2 l = __floats2half2_rn(x0 - b.x, x1 - b.y);
   hi = *reinterpret_cast<const uint32_t*>(&h);
+  const __half2 l = __floats2half2_rn(sub_half<0>(x0, hi), sub_half<1>(x1, hi));
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
