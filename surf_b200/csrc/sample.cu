@@ -135,45 +135,70 @@ k_sample_rays(const DevScene sc, const SampleCfg cfg, const float* __restrict__ 
 // render_core lines 75-89: section mid-points, voxel mask, compaction of valid points.
 // One thread per sample point.  Also writes the masked-out defaults (Q7): sdf = 100, grad = 0.
 // ---------------------------------------------------------------------------------------------
+// A block takes PF_K x 256 consecutive samples per iteration and reserves their list slots with ONE atomicAdd (a
+// warp-level reservation is 2 M atomics on one address per image and was what the kernel waited for: 37 long-scoreboard
+// stalls per issue, 2.5 ms per image).
+#define PF_K 8
 __global__ void __launch_bounds__(256)
 k_point_flags(const DevScene sc, const float* __restrict__ rays_o, const float* __restrict__ rays_d,
               const float* __restrict__ z_vals, int64_t B, int S, float sample_dist, int chunk_rays,
               float* __restrict__ mid_out, uint8_t* __restrict__ flags, float* __restrict__ sdf_out,
               float* __restrict__ grad_out, int32_t* __restrict__ list, int32_t* __restrict__ counter,
               int32_t* __restrict__ chunk_any) {
+  __shared__ int s_cnt[PF_K * 8];        // valid samples of (k, warp); then their exclusive prefix
+  __shared__ int s_base;
   const int64_t P = B * S;
-  const int lane = threadIdx.x & 31;
-  for (int64_t base = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) - lane; base < P;
-       base += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t p = base + lane;
-    bool valid = false;
-    if (p < P) {
-      const int64_t r = p / S;
-      const int j = (int)(p - r * S);
-      const float z = z_vals[p];
-      const float dist = (j + 1 < S) ? __fsub_rn(z_vals[p + 1], z) : sample_dist;
-      const float mid = __fadd_rn(z, __fmul_rn(dist, 0.5f));
-      const float px = ray_at(rays_o[r * 3], rays_d[r * 3], mid);
-      const float py = ray_at(rays_o[r * 3 + 1], rays_d[r * 3 + 1], mid);
-      const float pz = ray_at(rays_o[r * 3 + 2], rays_d[r * 3 + 2], mid);
-      valid = scene_point_mask(sc, px, py, pz);
-      if (mid_out) mid_out[p] = mid;
-      flags[p] = valid ? 3 : 0;          // bit0 voxel mask, bit1 computed
-      if (sdf_out) sdf_out[p] = 100.0f;
-      if (grad_out) {
-        grad_out[p * 3] = 0.f;
-        grad_out[p * 3 + 1] = 0.f;
-        grad_out[p * 3 + 2] = 0.f;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int64_t base = (int64_t)blockIdx.x * (PF_K * 256); base < P; base += (int64_t)gridDim.x * (PF_K * 256)) {
+    unsigned bal[PF_K];
+#pragma unroll
+    for (int k = 0; k < PF_K; ++k) {
+      const int64_t p = base + k * 256 + threadIdx.x;
+      bool valid = false;
+      if (p < P) {
+        const int64_t r = p / S;
+        const int j = (int)(p - r * S);
+        const float z = z_vals[p];
+        const float dist = (j + 1 < S) ? __fsub_rn(z_vals[p + 1], z) : sample_dist;
+        const float mid = __fadd_rn(z, __fmul_rn(dist, 0.5f));
+        const float px = ray_at(rays_o[r * 3], rays_d[r * 3], mid);
+        const float py = ray_at(rays_o[r * 3 + 1], rays_d[r * 3 + 1], mid);
+        const float pz = ray_at(rays_o[r * 3 + 2], rays_d[r * 3 + 2], mid);
+        valid = scene_point_mask(sc, px, py, pz);
+        if (mid_out) mid_out[p] = mid;
+        flags[p] = valid ? 3 : 0;          // bit0 voxel mask, bit1 computed
+        if (sdf_out) sdf_out[p] = 100.0f;
+        if (grad_out) {
+          grad_out[p * 3] = 0.f;
+          grad_out[p * 3 + 1] = 0.f;
+          grad_out[p * 3 + 2] = 0.f;
+        }
+        if (valid) chunk_any[r / chunk_rays] = 1;
       }
-      if (valid) chunk_any[r / chunk_rays] = 1;
+      bal[k] = __ballot_sync(0xffffffffu, valid);
+      if (lane == 0) s_cnt[k * 8 + warp] = __popc(bal[k]);
     }
-    const unsigned bal = __ballot_sync(0xffffffffu, valid);
-    if (bal) {
-      int start = 0;
-      if (lane == 0) start = atomicAdd(counter, __popc(bal));
-      start = __shfl_sync(0xffffffffu, start, 0);
-      if (valid) list[start + __popc(bal & ((1u << lane) - 1))] = (int32_t)p;
+    __syncthreads();
+    if (warp == 0) {        // exclusive prefix over the 64 (k, warp) counts, one reservation for the block
+      const int a0 = s_cnt[2 * lane], a1 = s_cnt[2 * lane + 1];
+      int v = a0 + a1;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+      }
+      const int total = __shfl_sync(0xffffffffu, v, 31);
+      s_cnt[2 * lane] = v - a0 - a1;
+      s_cnt[2 * lane + 1] = v - a1;
+      if (lane == 0) s_base = total ? atomicAdd(counter, total) : 0;
     }
+    __syncthreads();
+    const int start = s_base;
+#pragma unroll
+    for (int k = 0; k < PF_K; ++k)
+      if ((bal[k] >> lane) & 1u)
+        list[start + s_cnt[k * 8 + warp] + __popc(bal[k] & ((1u << lane) - 1))] = (int32_t)(base + k * 256 + threadIdx.x);
+    __syncthreads();        // s_cnt / s_base are rewritten by the next iteration
   }
 }
 
@@ -274,7 +299,7 @@ int surf_flags_pass(const surf_scene* s, const surf_render_cfg* cfg, const float
   const float sample_dist = 2.0f / (float)cfg->n_samples[0];
   const int64_t P = B * S;
   surf_time_begin(5, st);
-  k_point_flags<<<blocks_for(P, 256, 8), 256, 0, st>>>(s->dev, d_rays_o, d_rays_d, d_z_vals, B, S, sample_dist,
+  k_point_flags<<<blocks_for((P + PF_K - 1) / PF_K, 256, 8), 256, 0, st>>>(s->dev, d_rays_o, d_rays_d, d_z_vals, B, S, sample_dist,
                                                        chunk_rays, d_mid, d_flags, d_sdf, d_grad, d_list, d_counter,
                                                        d_chunk_any);
   surf_time_end(5, st);
