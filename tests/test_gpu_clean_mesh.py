@@ -158,7 +158,7 @@ def test_clean_mesh_end_to_end(min_visible):
     assert float(np.abs(gv).max()) < 0.75
 
 
-def test_clean_mesh_without_a_gpu_tensor_input_types():
+def test_clean_mesh_input_types():
     v, t = _blob_mesh(40)
     masks, intrs, c2ws = _views(3, 30, 40)
     m4 = masks[..., None].repeat(1, 1, 1, 3)             # (nv,H,W,C) masks are averaged over C (clean_mesh.py:116)
