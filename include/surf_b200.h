@@ -387,6 +387,12 @@ size_t surf_mesh_components_workspace_bytes(int64_t n_faces);
 int surf_mesh_components(const int32_t* d_faces, int64_t n_faces, int32_t min_len, void* d_workspace,
                          size_t workspace_bytes, int32_t* d_label, uint8_t* d_keep, void* stream);
 
+/* Host helper (no device work): advance torch's CPU mt19937 state by n_draws 32-bit draws without producing them
+ * (one float32 of torch.rand = one draw).  The pointers address the fields of the blob torch.get_rng_state() returns
+ * (CPUGeneratorImplStateLegacy: `left` int32 at byte 8, `next` uint64 at 16, `state[624]` uint64 at 24).  Used to keep
+ * the reference's sequential jitter stream (implicit_surface.py:276,305,174) when an image is ray-sharded over ranks. */
+int surf_mt19937_skip(uint64_t* h_state624, int32_t* h_left, uint64_t* h_next, uint64_t n_draws);
+
 int surf_version(void);
 const char* surf_last_error(void);
 /* number of kernel launches issued by this library in this process (bench.py's gpu_launches) */

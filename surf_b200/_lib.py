@@ -35,6 +35,7 @@ EXPORTS = [
     "surf_sdf_points", "surf_sdf_grid", "surf_sdf_full", "surf_sdf_smooth",
     "surf_mask_dilate", "surf_mesh_vertex_visibility", "surf_mesh_raster_workspace_bytes", "surf_mesh_first_hits",
     "surf_mesh_components_workspace_bytes", "surf_mesh_components",
+    "surf_mt19937_skip",
     "surf_point_mask", "surf_lookup_sparse", "surf_lookup_feature", "surf_blend", "surf_point_flags",
     "surf_tc_selftest",
     "surf_mc_workspace_bytes", "surf_mc_count", "surf_mc_emit",
@@ -206,6 +207,8 @@ def _declare(lib):
     lib.surf_sdf_points.argtypes = [vp, vp, vp, i64, vp, vp, i32, vp]
     lib.surf_sdf_full.restype = C.c_int
     lib.surf_sdf_full.argtypes = [vp, vp, vp, i64, vp, i32, vp]
+    lib.surf_mt19937_skip.restype = C.c_int
+    lib.surf_mt19937_skip.argtypes = [vp, vp, vp, C.c_uint64]
     lib.surf_mask_dilate.restype = C.c_int
     lib.surf_mask_dilate.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp]
     lib.surf_mesh_vertex_visibility.restype = C.c_int

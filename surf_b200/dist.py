@@ -127,23 +127,67 @@ def render_image_sharded(module, scene, rays_o, rays_d, near, far, cos_anneal_ra
         mine = jitter.next()
     else:
         if t_rand is None and module.perturb > 0:
-            t_rand = module.draw_chunk_randoms(n, chunk)
-        mine = None if t_rand is None else t_rand[r0:r1]
+            mine = draw_shard_randoms(module, n, r0, r1, chunk)
+        else:
+            mine = None if t_rand is None else t_rand[r0:r1]
     if near.shape[0] != 1:
         near, far = near[r0:r1], far[r0:r1]
     res = module.render_image(scene, rays_o[r0:r1], rays_d[r0:r1], near, far, cos_anneal_ratio, chunk, mine)
     return gather_image(res, n, chunk)
 
 
+def skip_cpu_rng(n_draws: int) -> None:
+    """Advance torch's global CPU generator by ``n_draws`` float32 draws without producing them (== discarding
+    ``torch.rand(n_draws)``, bit for bit, ~7x faster: only the mt19937 state transition runs, in the C library)."""
+    import ctypes as C
+
+    import numpy as np
+
+    from . import _lib
+    if n_draws <= 0:
+        return
+    st = torch.get_rng_state()
+    if st.numel() != 5056:
+        torch.rand(int(n_draws))            # an unknown state layout: draw and discard
+        return
+    buf = st.numpy()                        # CPUGeneratorImplStateLegacy: seed u64 | left i32 | seeded i32 | next u64 | state[624] u64
+    if int(buf[12:16].view(np.int32)[0]) == 0:
+        torch.rand(1)                       # not seeded yet: let torch seed it, then skip the rest
+        return skip_cpu_rng(n_draws - 1)
+    base = buf.ctypes.data
+    _lib.check(_lib.load().surf_mt19937_skip(C.c_void_p(base + 24), C.c_void_p(base + 8), C.c_void_p(base + 16),
+                                             C.c_uint64(int(n_draws))), "mt19937_skip")
+    torch.set_rng_state(st)
+
+
+def _chunk_draws(module, n_rays: int, chunk: int) -> int:
+    """Draws the chunks of ``n_rays`` rays consume (ImplicitSurface.draw_chunk_randoms)."""
+    from .modules.implicit_surface import N_RANDOM_PTS
+    n_st = len(module.n_samples)
+    full, rem = divmod(n_rays, chunk)
+    return full * (n_st * chunk + N_RANDOM_PTS * 3) + ((n_st * rem + N_RANDOM_PTS * 3) if rem else 0)
+
+
+def draw_shard_randoms(module, n_rays: int, r0: int, r1: int, chunk: int = 256) -> torch.Tensor:
+    """Jitter table (r1-r0, n_stages) of the rays [r0, r1) of an n_rays image, leaving the global CPU generator where
+    the single-process image pass leaves it: the draws of the other chunks are skipped, not produced."""
+    assert (r0 % chunk == 0 or r0 == n_rays) and (r1 % chunk == 0 or r1 == n_rays), "shard borders must sit on chunk boundaries"
+    skip_cpu_rng(_chunk_draws(module, r0, chunk))
+    t = module.draw_chunk_randoms(r1 - r0, chunk) if r1 > r0 else torch.empty((0, len(module.n_samples)))
+    skip_cpu_rng(_chunk_draws(module, n_rays - r1, chunk))
+    return t
+
+
 class JitterPrefetcher:
     """The jitter tables of consecutive images for ONE rank's ray shard, drawn a step ahead on a worker thread.
 
     The reference draws its jitter from torch's global CPU generator, sequentially over the image (quirk Q1): 4 x
-    rand([256,1]) + rand([1024,3]) per 256-ray chunk, 7.4 M draws (~20 ms of mt19937) per 576x800 image.  To render a
-    shard bit-identically to the single-GPU image a rank has to consume the draws of the chunks before its shard, draw
-    its own, and consume the rest so that the NEXT image starts at the right place of the stream.  Done inline that is
-    ~20 ms of host time per image on every rank — more than the 17 ms an 8-GPU image takes on the device.  Here a
-    worker thread does it for image k+1 while the GPU renders image k; `next()` hands out a pinned (r1-r0, n_stages)
+    rand([256,1]) + rand([1024,3]) per 256-ray chunk, 7.4 M draws per 576x800 image.  To render a shard
+    bit-identically to the single-GPU image a rank has to consume the draws of the chunks before its shard, draw its
+    own, and consume the rest so that the NEXT image starts at the right place of the stream.  Producing all of them
+    with torch.rand is ~20 ms of host time per image on every rank — more than the 15 ms an 8-GPU image takes on the
+    device; draw_shard_randoms skips the foreign chunks in the C library (state transition only, ~3 ms) and a worker
+    thread does even that for image k+1 while the GPU renders image k; `next()` hands out a pinned (r1-r0, n_stages)
     table.  The worker is the only consumer of the global generator while the prefetcher is open (seed before creating
     it; close() it before drawing anything else)."""
 
@@ -157,23 +201,10 @@ class JitterPrefetcher:
         self._t = threading.Thread(target=self._work, name="surf-jitter", daemon=True)
         self._t.start()
 
-    def _draws(self, n_rays: int) -> int:          # draws the chunks of n_rays rays consume (draw_chunk_randoms)
-        n_st = len(self._m.n_samples)
-        full, rem = divmod(n_rays, self._chunk)
-        from .modules.implicit_surface import N_RANDOM_PTS
-        return full * (n_st * self._chunk + N_RANDOM_PTS * 3) + ((n_st * rem + N_RANDOM_PTS * 3) if rem else 0)
-
     def _work(self):
         try:
             while not self._stop.is_set():
-                if self._r0:
-                    torch.rand(self._draws(self._r0))                      # the chunks before my shard
-                if self._r1 > self._r0:
-                    t = self._m.draw_chunk_randoms(self._r1 - self._r0, self._chunk)
-                else:
-                    t = torch.empty((0, len(self._m.n_samples)))
-                if self._n > self._r1:
-                    torch.rand(self._draws(self._n - self._r1))            # ... and after it
+                t = draw_shard_randoms(self._m, self._n, self._r0, self._r1, self._chunk)
                 if self._pin:
                     t = t.pin_memory()
                 while not self._stop.is_set():

@@ -89,3 +89,27 @@ def test_jitter_prefetcher_reproduces_the_sequential_stream():
                     got = pf.next()
                     assert got.shape == (r1 - r0, 4)
                     assert torch.equal(got, want[k][r0:r1]), (world, rank, k)
+
+
+def test_skip_cpu_rng_equals_drawing_and_discarding():
+    """surf_mt19937_skip advances torch's CPU generator exactly like torch.rand(n) does (state blob and the following
+    draws), for counts around the 624-word twist boundaries and for image-sized skips."""
+    import time
+    import torch
+    from surf_b200.dist import skip_cpu_rng
+    for seed, pre, n in [(0, 0, 1), (1, 0, 623), (2, 0, 624), (3, 0, 625), (4, 5, 619), (5, 5, 620), (6, 700, 1248),
+                         (7, 3, 1_000_003), (8, 0, 7_372_800)]:
+        torch.manual_seed(seed)
+        if pre:
+            torch.rand(pre)
+        torch.rand(n)
+        want_state, want_next = torch.get_rng_state().clone(), torch.rand(1000)
+        torch.manual_seed(seed)
+        if pre:
+            torch.rand(pre)
+        skip_cpu_rng(n)
+        assert torch.equal(torch.get_rng_state(), want_state), (seed, pre, n)
+        assert torch.equal(torch.rand(1000), want_next), (seed, pre, n)
+    torch.manual_seed(0)
+    t0 = time.perf_counter(); torch.rand(7_372_800); t1 = time.perf_counter(); skip_cpu_rng(7_372_800); t2 = time.perf_counter()
+    print("7.37 M draws: torch.rand %.1f ms, skip %.1f ms" % ((t1 - t0) * 1e3, (t2 - t1) * 1e3))
