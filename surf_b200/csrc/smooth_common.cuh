@@ -173,3 +173,60 @@ __device__ __forceinline__ void sparse_back_fused(const DevScene& sc, int l, flo
   gd3[0] = hz * C.inv; gd3[1] = hy * C.inv; gd3[2] = hx * C.inv;
   m3[0] = mz; m3[1] = my; m3[2] = mx;
 }
+
+// first-order reverse pass of one level, batched loads: g3 = J_feat^T g / vs (world xyz)
+__device__ __forceinline__ void sparse_back_first(const DevScene& sc, int l, float px, float py, float pz, const float* g,
+                                                  float* g3) {
+  SparseCorners C;
+  sparse_corners(sc, l, px, py, pz, C);
+  float gx = 0.f, gy = 0.f, gz = 0.f;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    float4 a[4], b[4];
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+      const int32_t row = C.row[h * 4 + cc] < 0 ? 0 : C.row[h * 4 + cc];
+      a[cc] = __ldg(sc.vol8[l] + (size_t)row * 2);
+      b[cc] = __ldg(sc.vol8[l] + (size_t)row * 2 + 1);
+    }
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+      const int c = h * 4 + cc;
+      if (C.row[c] < 0) continue;
+      const float wx = (c & 1) ? C.wx1 : C.wx0, wy = (c & 2) ? C.wy1 : C.wy0, wz = (c & 4) ? C.wz1 : C.wz0;
+      const float sx = (c & 1) ? 1.f : -1.f, sy = (c & 2) ? 1.f : -1.f, sz = (c & 4) ? 1.f : -1.f;
+      const float4 A = a[cc], B = b[cc];
+      const float s = A.x * g[0] + A.y * g[1] + A.z * g[2] + A.w * g[3] + B.x * g[4] + B.y * g[5] + B.z * g[6];
+      gx += s * (sx * wy * wz); gy += s * (sy * wx * wz); gz += s * (sz * wx * wy);
+    }
+  }
+  g3[0] = gz * C.inv; g3[1] = gy * C.inv; g3[2] = gx * C.inv;          // world x <- grid z (projector.py:379)
+}
+
+// value only (forward), batched loads
+__device__ __forceinline__ void sparse_value_batched(const DevScene& sc, int l, float px, float py, float pz, float* f7) {
+  SparseCorners C;
+  sparse_corners(sc, l, px, py, pz, C);
+#pragma unroll
+  for (int c = 0; c < 7; ++c) f7[c] = 0.f;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    float4 a[4], b[4];
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+      const int32_t row = C.row[h * 4 + cc] < 0 ? 0 : C.row[h * 4 + cc];
+      a[cc] = __ldg(sc.vol8[l] + (size_t)row * 2);
+      b[cc] = __ldg(sc.vol8[l] + (size_t)row * 2 + 1);
+    }
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+      const int c = h * 4 + cc;
+      if (C.row[c] < 0) continue;
+      const float wx = (c & 1) ? C.wx1 : C.wx0, wy = (c & 2) ? C.wy1 : C.wy0, wz = (c & 4) ? C.wz1 : C.wz0;
+      const float w = wx * wy * wz;
+      const float v[7] = {a[cc].x, a[cc].y, a[cc].z, a[cc].w, b[cc].x, b[cc].y, b[cc].z};
+#pragma unroll
+      for (int k = 0; k < 7; ++k) f7[k] += v[k] * w;
+    }
+  }
+}
