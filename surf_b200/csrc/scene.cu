@@ -110,7 +110,7 @@ extern "C" int64_t surf_launch_count(void) { return (int64_t)g_launches.load(); 
 // conversion kernels (HBM-bound streaming; 128-bit accesses where the layout allows)
 // ---------------------------------------------------------------------------------------------
 __global__ void k_index64_to_32(const longlong2* __restrict__ in, int2* __restrict__ out, size_t n_pairs,
-                                const int64_t* __restrict__ in1, int32_t* __restrict__ out1, size_t n) {
+                                const int64_t* in1, int32_t* out1, size_t n) {   // (same buffers: the odd last element)
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t p = i; p < n_pairs; p += stride) {

@@ -152,7 +152,7 @@ template <bool GRAD, int SKIP, bool HEAD>
 __device__ __forceinline__ void t2_fwd_act(const T2Epi& c, int cb, const uint32_t (&d)[8], float (&h)[8], uint4& spw,
                                            uint32_t& sgn, float& head) {
   float cw[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  if (SKIP == 0 && !HEAD) {
+  if constexpr (SKIP == 0 && !HEAD) {
     // plain hidden columns, two at a time on the packed fp32x2 pipe (FMUL2 / FADD2 / FFMA2: 9 instructions per pair
     // instead of 12; the same IEEE operations per element, so the results are bit-identical to the scalar form below)
 #pragma unroll
@@ -176,8 +176,7 @@ __device__ __forceinline__ void t2_fwd_act(const T2Epi& c, int cb, const uint32_
     if (GRAD)
       spw = make_uint4(t2_code_pair(cw[0], cw[1]), t2_code_pair(cw[2], cw[3]), t2_code_pair(cw[4], cw[5]),
                        t2_code_pair(cw[6], cw[7]));
-    return;
-  }
+  } else {
 #pragma unroll
   for (int n = 0; n < 8; ++n) {
     const bool pe = (SKIP == 2) || (SKIP == 1 && n >= 5);
@@ -204,6 +203,7 @@ __device__ __forceinline__ void t2_fwd_act(const T2Epi& c, int cb, const uint32_
   if (GRAD && !HEAD)
     spw = make_uint4(t2_code_pair(cw[0], cw[1]), t2_code_pair(cw[2], cw[3]), t2_code_pair(cw[4], cw[5]),
                      t2_code_pair(cw[6], cw[7]));
+  }
 }
 
 // Reverse activation of my 8 columns of one group: v = delta_{l-1} = D * softplus'(z_{l-1}); the sign of element n is
@@ -212,7 +212,7 @@ template <int SKIP>
 __device__ __forceinline__ void t2_bwd_act(const T2Epi& c, int cb, const uint32_t (&d)[8], const uint4& spw, uint32_t sgn,
                                            float (&v)[8]) {
   const uint32_t sp[4] = {spw.x, spw.y, spw.z, spw.w};
-  if (SKIP == 0) {
+  if constexpr (SKIP == 0) {
     // two columns at a time: 1 - rr and the product on the packed fp32x2 pipe (same operations per element)
 #pragma unroll
     for (int n = 0; n < 8; n += 2) {
@@ -224,8 +224,7 @@ __device__ __forceinline__ void t2_bwd_act(const T2Epi& c, int cb, const uint32_
       v[n] = vv.x;
       v[n + 1] = vv.y;
     }
-    return;
-  }
+  } else {
 #pragma unroll
   for (int n = 0; n < 8; ++n) {
     const bool pe = (SKIP == 2) || (SKIP == 1 && n >= 5);
@@ -238,6 +237,7 @@ __device__ __forceinline__ void t2_bwd_act(const T2Epi& c, int cb, const uint32_
       const bool neg = ((sgn >> (31 - n)) & 1u) != 0u;
       v[n] = g * (neg ? 1.0f - rr : rr);
     }
+  }
   }
 }
 
