@@ -45,6 +45,8 @@ def vertex_visibility(vertices: torch.Tensor, masks: torch.Tensor, intrs, c2ws) 
     w2c = np.ascontiguousarray(torch.linalg.inv(c2w)[:, :3, :].numpy(), dtype=np.float32)      # (nv,3,4) host
     K = np.ascontiguousarray(_host_f32(intrs)[:, :3, :3])
     count = torch.empty(v.shape[0], dtype=torch.int32, device=v.device)
+    if v.shape[0] == 0:
+        return count
     with torch.cuda.device(v.device):
         _lib.check(_lib.load().surf_mesh_vertex_visibility(v.data_ptr(), v.shape[0], w2c.ctypes.data, K.ctypes.data, nv,
                                                            m.data_ptr(), h, w, count.data_ptr(), _stream()),
@@ -67,6 +69,8 @@ def first_hit_faces(vertices: torch.Tensor, faces: torch.Tensor, masks: torch.Te
     K = np.ascontiguousarray(_host_f32(intrs)[:, :3, :3])
     hit = torch.zeros(max(1, f.shape[0]), dtype=torch.uint8, device=v.device)
     stats = torch.zeros(2, dtype=torch.int32, device=v.device)
+    if f.shape[0] == 0:                  # nothing to hit: every masked ray misses
+        return hit[:0].bool(), int((m > 0).sum()) * int(upscale) ** 2
     with torch.cuda.device(v.device):
         nbytes = int(lib.surf_mesh_raster_workspace_bytes(hs, ws_))
         wsb = torch.empty(nbytes, dtype=torch.uint8, device=v.device)

@@ -136,9 +136,9 @@ __global__ void k_vertex_visibility(const float* __restrict__ verts, int64_t nve
 extern "C" int surf_mesh_vertex_visibility(const float* d_vertices, int64_t n_vertices, const float* h_w2c,
                                            const float* h_K, int32_t n_views, const uint8_t* d_masks, int32_t h,
                                            int32_t w, int32_t* d_count, void* stream) {
+  if (n_vertices <= 0) return 0;
   SURF_CHECK_ARG(d_vertices && h_w2c && h_K && d_masks && d_count, "null pointer");
   SURF_CHECK_ARG(n_views >= 1, "n_views");
-  if (n_vertices <= 0) return 0;
   // the view parameters travel as a kernel argument: SURF_MAX_VIEWS + 1 views per launch, counts accumulated
   for (int v0 = 0; v0 < n_views; v0 += SURF_MAX_VIEWS + 1) {
     MeshViews V;

@@ -177,3 +177,21 @@ def test_runner_validate_writes_reference_artifacts(tmp_path):
     assert rd.shape == hw
     assert_close(rd, g["out"]["render_depth"], 2e-3, "render depth written by the runner vs the reference image", floor=1e-2)
     assert "psnr" in scalars and "color_loss" in scalars
+
+
+def test_invalid_colour_path_is_rejected_and_empty_second_order_call():
+    g, sc, m, d = _setup()
+    i = g["in"]
+    ps = m.prepare(d.matching_volume, d.volumes, d.sparse_idxes, d.mask_volumes, d.imgs, d.features, d.intrs, d.c2ws)
+    m.color_path = 7
+    with pytest.raises(RuntimeError):
+        m.render(i["rays_o"].to(DEV), i["rays_d"].to(DEV), i["near"].to(DEV), i["far"].to(DEV), ps, None, None, None, None,
+                 None, None, d.intrs, d.c2ws, 1.0, None)
+    m.color_path = _lib.COLOR_SERIAL
+    empty = torch.zeros((0, 3), device=DEV)
+    assert m.sdf_network.smooth(empty, ps).shape == (0, 3)
+    for mode in (_lib.MLP_TC, _lib.MLP_FFMA):
+        gr, sm = m.sdf_network.smooth(empty, ps, with_grad=True, mode=mode)
+        assert gr.shape == (0, 3) and sm.shape == (0, 3)
+    with pytest.raises(RuntimeError):
+        m.sdf_network.smooth(torch.zeros((4, 3), device=DEV), ps, mode=3)

@@ -165,3 +165,22 @@ def test_clean_mesh_input_types():
     a = CM.clean_mesh(torch.from_numpy(v), torch.from_numpy(t), m4, intrs, c2ws, 2, 1, 2, 100)
     b = CM.clean_mesh(v, t, masks, intrs, c2ws, 2, 1, 2, 100)
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+def test_degenerate_inputs():
+    """Empty meshes, meshes that lose every face, masks that select nothing."""
+    masks, intrs, c2ws = _views(2, 24, 32)
+    v0, t0 = np.zeros((0, 3)), np.zeros((0, 3), dtype=np.int64)
+    gv, gt = CM.clean_mesh(v0, t0, masks, intrs, c2ws, 2, 1, 2, 10)
+    assert gv.shape == (0, 3) and gt.shape == (0, 3)
+    v, t = _blob_mesh(32)
+    gv, gt = CM.clean_mesh(v, t, torch.zeros_like(masks), intrs, c2ws, 2, 1, 2, 10)       # nothing is visible anywhere
+    assert gv.shape == (0, 3) and gt.shape == (0, 3)
+    gv, gt = CM.clean_mesh(v, t, masks, intrs, c2ws, 2, 1, 2, 10 ** 9)                     # no component is large enough
+    assert gv.shape == (0, 3) and gt.shape == (0, 3)
+    label, keep = CM.face_components(torch.zeros((0, 3), dtype=torch.int64, device=DEV), 5)
+    assert label.numel() == 0 and keep.numel() == 0
+    # faces that share no edge are not nodes of the adjacency graph: never kept, whatever min_len
+    iso = torch.tensor([[0, 1, 2], [3, 4, 5]], device=DEV)
+    _, keep = CM.face_components(iso, 1)
+    assert not bool(keep.any())
