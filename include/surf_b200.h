@@ -387,6 +387,29 @@ size_t surf_mesh_components_workspace_bytes(int64_t n_faces);
 int surf_mesh_components(const int32_t* d_faces, int64_t n_faces, int32_t min_len, void* d_workspace,
                          size_t workspace_bytes, int32_t* d_label, uint8_t* d_keep, void* stream);
 
+/* ---- 2-D feature pyramid (FeatureNetwork, models/modules/feature_network.py:126-178) ----
+ * NCHW fp32 tensors.  The InstanceNorm2d + ReLU that follows every convolution is not materialised: a convolution
+ * leaves the (sum, sum of squares) of every thread block's raw outputs per (image, channel) in d_partials — fp64 pairs,
+ * [n * c_out planes][blocks per image], blocks per image = surf_fpn_conv_blocks / surf_fpn_deconv_blocks of the OUTPUT
+ * size — surf_fpn_finish_stats sums them in a fixed order into (mean, 1/sqrt(var + eps)) pairs, and the consumer passes
+ * those as d_in_stats to have relu((x - mean) * rstd) applied while it loads (NULL: the input is a plain tensor).
+ *   surf_fpn_conv3x3        nn.Conv2d(c_in, c_out, 3, stride, padding 1, bias=False); c_out in {4, 8, 16, 32, 64};
+ *                           d_partials may be NULL (output layers)
+ *   surf_fpn_deconv3x3s2    nn.ConvTranspose2d(c_in, c_out, 3, stride 2, padding 1, output_padding 1, bias=False):
+ *                           (h, w) -> (2h, 2w); weight (c_in, c_out, 3, 3); c_out in {8, 16, 32}
+ *   surf_fpn_norm_relu_add  d_out = relu(norm(a)) + relu(norm(b))  (decoder output, feature_network.py:166); b NULL:
+ *                           d_out = relu(norm(a)) */
+int32_t surf_fpn_conv_blocks(int32_t h_out, int32_t w_out);
+int32_t surf_fpn_deconv_blocks(int32_t h_out, int32_t w_out);
+int surf_fpn_conv3x3(const float* d_x, const float* d_in_stats, const float* d_weight, int32_t n, int32_t c_in, int32_t h,
+                     int32_t w, int32_t c_out, int32_t stride, float* d_out, double* d_partials, void* stream);
+int surf_fpn_deconv3x3s2(const float* d_x, const float* d_in_stats, const float* d_weight, int32_t n, int32_t c_in,
+                         int32_t h, int32_t w, int32_t c_out, float* d_out, double* d_partials, void* stream);
+int surf_fpn_finish_stats(const double* d_partials, int32_t n_planes, int32_t blocks_per_plane, int64_t pixels_per_plane,
+                          float eps, float* d_stats, void* stream);
+int surf_fpn_norm_relu_add(const float* d_a, const float* d_stats_a, const float* d_b, const float* d_stats_b,
+                           int32_t n_planes, int64_t pixels_per_plane, float* d_out, void* stream);
+
 /* Host helper (no device work): advance torch's CPU mt19937 state by n_draws 32-bit draws without producing them
  * (one float32 of torch.rand = one draw).  The pointers address the fields of the blob torch.get_rng_state() returns
  * (CPUGeneratorImplStateLegacy: `left` int32 at byte 8, `next` uint64 at 16, `state[624]` uint64 at 24).  Used to keep

@@ -241,6 +241,20 @@ def case_volume(IS, name, nv, H, W, base, scene_seed, weight_seed):
     save(name, recipe, _Agg(), {}, out)
 
 
+def case_fpn(IS, name, nv, H, W, weight_seed, img_seed):
+    """FeatureNetwork.forward (feature_network.py:126-178) of the unmodified reference: 4-stage encoder / decoder with
+    InstanceNorm, d_base 8, d_out [4,4,4,4] (confs/surf.conf)."""
+    from models.modules.feature_network import FeatureNetwork
+    conf = ref_loader.DictConf({"d_in": 3, "d_base": 8, "d_out": [4, 4, 4, 4]})
+    torch.manual_seed(weight_seed)
+    net = FeatureNetwork(conf).eval()
+    imgs = torch.rand((nv, 3, H, W), generator=torch.Generator().manual_seed(img_seed))
+    with torch.no_grad():
+        outs = net(imgs)
+    save(name, dict(nv=nv, H=H, W=W, weight_seed=weight_seed, img_seed=img_seed), net, {"imgs": imgs},
+         {"feat%d" % i: o for i, o in enumerate(outs)})
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     IS = ref_loader.load_reference()
@@ -266,6 +280,8 @@ def main():
     case_matching_field(IS, "matching_field", nv=3, H=48, W=64, base=8, scene_seed=1, torch_seed=9)
     # H: the producers of the scene tensors: Volume.*
     case_volume(IS, "volume", nv=3, H=48, W=64, base=8, scene_seed=1, weight_seed=4)
+    # I: the 2-D feature pyramid (first half)
+    case_fpn(IS, "fpn", nv=2, H=40, W=56, weight_seed=5, img_seed=6)
 
 
 if __name__ == "__main__":

@@ -36,6 +36,8 @@ EXPORTS = [
     "surf_mask_dilate", "surf_mesh_vertex_visibility", "surf_mesh_raster_workspace_bytes", "surf_mesh_first_hits",
     "surf_mesh_components_workspace_bytes", "surf_mesh_components",
     "surf_mt19937_skip",
+    "surf_fpn_conv_blocks", "surf_fpn_deconv_blocks", "surf_fpn_conv3x3", "surf_fpn_deconv3x3s2", "surf_fpn_finish_stats",
+    "surf_fpn_norm_relu_add",
     "surf_point_mask", "surf_lookup_sparse", "surf_lookup_feature", "surf_blend", "surf_point_flags",
     "surf_tc_selftest",
     "surf_mc_workspace_bytes", "surf_mc_count", "surf_mc_emit",
@@ -207,6 +209,18 @@ def _declare(lib):
     lib.surf_sdf_points.argtypes = [vp, vp, vp, i64, vp, vp, i32, vp]
     lib.surf_sdf_full.restype = C.c_int
     lib.surf_sdf_full.argtypes = [vp, vp, vp, i64, vp, i32, vp]
+    lib.surf_fpn_conv3x3.restype = C.c_int
+    lib.surf_fpn_conv3x3.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp]
+    lib.surf_fpn_deconv3x3s2.restype = C.c_int
+    lib.surf_fpn_deconv3x3s2.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp]
+    lib.surf_fpn_finish_stats.restype = C.c_int
+    lib.surf_fpn_finish_stats.argtypes = [vp, i32, i32, i64, f32, vp, vp]
+    lib.surf_fpn_conv_blocks.restype = C.c_int32
+    lib.surf_fpn_conv_blocks.argtypes = [i32, i32]
+    lib.surf_fpn_deconv_blocks.restype = C.c_int32
+    lib.surf_fpn_deconv_blocks.argtypes = [i32, i32]
+    lib.surf_fpn_norm_relu_add.restype = C.c_int
+    lib.surf_fpn_norm_relu_add.argtypes = [vp, vp, vp, vp, i32, i64, vp, vp]
     lib.surf_mt19937_skip.restype = C.c_int
     lib.surf_mt19937_skip.argtypes = [vp, vp, vp, C.c_uint64]
     lib.surf_mask_dilate.restype = C.c_int

@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB = os.path.join(CSRC, "libsurf_b200.so")
-SOURCES = ["scene.cu", "sample.cu", "sdf_mlp.cu", "blend.cu", "render.cu", "tc_selftest.cu", "sdf_tc2.cu", "blend_tc.cu", "marching.cu", "mesh_clean.cu", "extras.cu", "sdf_smooth.cu", "sdf_smooth_tc.cu", "matching.cu", "volume.cu", "host_rng.cu"]
+SOURCES = ["scene.cu", "sample.cu", "sdf_mlp.cu", "blend.cu", "render.cu", "tc_selftest.cu", "sdf_tc2.cu", "blend_tc.cu", "marching.cu", "mesh_clean.cu", "extras.cu", "sdf_smooth.cu", "sdf_smooth_tc.cu", "matching.cu", "volume.cu", "host_rng.cu", "fpn.cu"]
 EXTRA = os.environ.get("SURF_NVCC_EXTRA", "").split()
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 

@@ -180,3 +180,15 @@ def test_volume_producers_match_the_reference():
     mv1, mk1 = O.volume_sparse2dense(o["reg1"][:, :1], c1[dm][m1], [2 * base] * 3, mv0)
     assert torch.equal(mv1, o["mv1"]) and torch.equal(mk1, o["mk1"])
     assert torch.equal(O.volume_get_index(c1[dm][m1], [2 * base] * 3), o["idx1"])
+
+
+def test_fpn_oracle_equals_the_reference_feature_network():
+    """oracle/fpn_oracle.py against the unmodified reference FeatureNetwork (tests/golden/fpn.npz)."""
+    import fpn_oracle
+    g = load_golden("fpn")
+    outs = fpn_oracle.feature_network_forward(g["sd"], g["in"]["imgs"])
+    assert len(outs) == 4
+    for i, o in enumerate(outs):
+        want = torch.from_numpy(g["out"]["feat%d" % i])
+        assert o.shape == want.shape == (2, 4, 40 // 2 ** (3 - i), 56 // 2 ** (3 - i))
+        assert torch.equal(o, want), "stage %d differs from the reference" % i
