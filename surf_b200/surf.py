@@ -3,15 +3,18 @@
 Scope: this class owns ``implicit_surface`` (same attribute name, so
 ``implicit_surface.*`` state_dict keys match the reference checkpoint) and dispatches ``forward`` to it
 with the scene lists reversed to renderer order (surf.py:159).  Volume construction
-(``build_volumes``: FPN + torchsparse cost-volume regularisation + matching field, surf.py:80-131) is
-upstream of the hot path and out of scope: scenes enter through ``set_volumes`` (the ``has_vol``
-branch of the reference, surf.py:149-157) in the reference's own coarse->fine layout.
+(``build_volumes``, surf.py:80-131) is upstream of the hot path: its pieces exist here as drop-in modules —
+``feature_network`` (the 2-D pyramid, ``modules/feature_network.py``), ``modules/volume.py`` and
+``modules/matching_field.py`` — except the torchsparse cost-volume regularisation (``reg_network``), so scenes still
+enter through ``set_volumes`` (the ``has_vol`` branch of the reference, surf.py:149-157) in the reference's own
+coarse->fine layout.
 """
 from __future__ import annotations
 
 import torch
 import torch.nn as nn
 
+from .modules.feature_network import FeatureNetwork
 from .modules.implicit_surface import ImplicitSurface
 
 
@@ -22,6 +25,8 @@ class SuRF(nn.Module):
         self.range_ratios = confs.get_list("range_ratios", default=[1.0, 0.4, 0.1, 0.01])
         self.num_stage = len(self.range_ratios)
         self.implicit_surface = ImplicitSurface(confs["implicit_surface"])
+        # same attribute name as the reference (surf.py:25), so `feature_network.*` checkpoint keys load
+        self.feature_network = FeatureNetwork(confs["feature_network"]) if "feature_network" in confs else None
         self.volumes = None
         self.sparse_idxes = None
         self.mask_volmes = None        # (sic) attribute name of the reference, surf.py:74
@@ -41,6 +46,12 @@ class SuRF(nn.Module):
         self.matching_volume = matching_volume
         self.features = list(features)
         self.has_vol = True
+
+    def extract_features(self, imgs):
+        """``self.feature_network(imgs)`` of surf.py:69: coarse -> fine list of (nv, 4, H/2^i, W/2^i) feature maps."""
+        if self.feature_network is None:
+            raise RuntimeError("this SuRF was built from a conf without a feature_network block")
+        return self.feature_network(imgs)
 
     def init_volumes(self, ipts):
         raise NotImplementedError(

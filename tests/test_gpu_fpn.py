@@ -64,3 +64,28 @@ def test_full_size_images_and_errors():
         net(torch.rand(1, 3, 50, 64, device=DEV))
     with pytest.raises(RuntimeError):
         net(torch.rand(1, 3, 64, 64))
+
+
+def test_surf_model_owns_the_feature_network():
+    """SuRF built from a reference conf has `feature_network` under the reference's attribute name (surf.py:25), so the
+    `feature_network.*` keys of a reference checkpoint load; extract_features = surf.py:69."""
+    import os
+    from surf_b200.surf import SuRF
+    here = os.path.dirname(os.path.abspath(__file__))
+    c = conf.parse_file(os.path.join(here, "..", "surf_b200", "confs", "surf.conf")) if os.path.exists(
+        os.path.join(here, "..", "surf_b200", "confs", "surf.conf")) else None
+    if c is None:
+        c = conf.ConfigTree()
+        m = conf.ConfigTree()
+        m.put("range_ratios", [1.0, 0.4, 0.1, 0.01])
+        m.put("implicit_surface", conf.default_implicit_surface_conf())
+        m.put("feature_network", _conf())
+        c.put("model", m)
+    g = load_golden("fpn")
+    model = SuRF(c["model"])
+    model.feature_network.load_state_dict(g["sd"], strict=True)
+    assert {"feature_network." + k for k in g["sd"]} <= set(model.state_dict().keys())
+    model = model.to(DEV)
+    outs = model.extract_features(g["in"]["imgs"].to(DEV))
+    for i, o in enumerate(outs):
+        assert_close(o, g["out"]["feat%d" % i], 1e-4, "SuRF.extract_features stage %d" % i)
