@@ -195,3 +195,36 @@ def test_invalid_colour_path_is_rejected_and_empty_second_order_call():
         assert gr.shape == (0, 3) and sm.shape == (0, 3)
     with pytest.raises(RuntimeError):
         m.sdf_network.smooth(torch.zeros((4, 3), device=DEV), ps, mode=3)
+
+
+def test_runner_validate_with_clean_mesh(tmp_path):
+    """`--clean_mesh` (runner.py:233-234): the extracted mesh is cleaned against inputs["masks"] before it is written."""
+    from surf_b200.runner import validate
+    g = load_golden("validate_24x32")
+    sc = scene_from_recipe(g["recipe"])
+    model = _surf_model(g)
+    d = sc.to(DEV)
+    model.set_volumes(d.volumes[::-1], d.sparse_idxes[::-1], d.mask_volumes[::-1], d.matching_volume, d.features[::-1])
+    i = g["in"]
+    r = int(g["recipe"]["res_level"])
+    hw = (sc.H // r, sc.W // r)
+    yy, xx = torch.meshgrid(torch.arange(sc.H), torch.arange(sc.W), indexing="ij")
+    masks = ((xx - sc.W / 2) ** 2 + (yy - sc.H / 2) ** 2 <= (0.3 * sc.H) ** 2).float()[None].repeat(sc.nv, 1, 1)
+
+    def item():
+        return _ipts(d, i["rays_o"].to(DEV), i["rays_d"].to(DEV), bound_min=torch.tensor([-1.0, -1, -1]),
+                     bound_max=torch.tensor([1.0, 1, 1]), hw=hw, file_name="scan1_0", scene="scan1",
+                     scale_mat=torch.eye(4), color=torch.rand(hw[0] * hw[1], 3), masks=masks)
+
+    def n_faces(path):
+        with open(path, "rb") as f:
+            head = f.read(400).decode("latin1")
+        return int(head.split("element face ")[1].split("\n")[0])
+
+    torch.manual_seed(0)
+    validate(model, [item()], str(tmp_path / "a"), epoch=1, mesh_resolution=64)
+    torch.manual_seed(0)
+    validate(model, [item()], str(tmp_path / "b"), epoch=1, mesh_resolution=64, clean_mesh=True)
+    full = n_faces(os.path.join(tmp_path, "a", "meshes", "scan1_epoch1.ply"))
+    cleaned = n_faces(os.path.join(tmp_path, "b", "meshes", "scan1_epoch1.ply"))
+    assert 0 < cleaned < full, (cleaned, full)
