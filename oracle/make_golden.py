@@ -255,6 +255,66 @@ def case_fpn(IS, name, nv, H, W, weight_seed, img_seed):
          {"feat%d" % i: o for i, o in enumerate(outs)})
 
 
+def load_reference_surf():
+    """models/surf.py of the unmodified reference; `torchsparse` (2.1.0, un-vendored) is shimmed with a container
+    SparseTensor and inert layer classes — the regularisation network itself is replaced by oracle/standin_reg.py."""
+    import types
+    import torch.nn as nn
+    if "torchsparse" not in sys.modules:
+        ts, tsn, tst = types.ModuleType("torchsparse"), types.ModuleType("torchsparse.nn"), types.ModuleType("torchsparse.tensor")
+
+        class SparseTensor:
+            def __init__(self, feats, coords):
+                self.F, self.C = feats, coords
+        tst.SparseTensor = SparseTensor
+        for name in ("Conv3d", "BatchNorm", "ReLU"):
+            setattr(tsn, name, lambda *a, **k: nn.Identity())
+        ts.nn, ts.tensor = tsn, tst
+        sys.modules.update({"torchsparse": ts, "torchsparse.nn": tsn, "torchsparse.tensor": tst})
+    from models import surf as ref_surf
+    return ref_surf
+
+
+def case_build_volumes(IS, name, nv, H, W, base, scene_seed, weight_seed):
+    """SuRF.build_volumes (surf.py:80-131) of the unmodified reference — FeatureNetwork, Volume, MatchingField and the
+    four-stage orchestration — with the stand-in regulariser of oracle/standin_reg.py in place of the torchsparse net."""
+    import standin_reg
+    ref_surf = load_reference_surf()
+    sc = synthetic.make_scene(nv, H, W, base, seed=scene_seed)
+    model_conf = ref_loader.DictConf({
+        "range_ratios": [1.0, 0.4, 0.1, 0.01],
+        "feature_network": ref_loader.DictConf({"d_in": 3, "d_base": 8, "d_out": [4, 4, 4, 4]}),
+        "volume": ref_loader.DictConf({"base_volume_dim": [base, base, base]}),
+        "reg_network": ref_loader.DictConf({"d_in": [8, 16, 16, 16], "d_base": [8, 8, 8, 8], "d_out": [8, 8, 8, 8]}),
+        "matching_field": ref_loader.DictConf({"n_samples_depths": [128, 64, 32, 16], "n_importance_depths": [128, 64, 32, 16],
+                                               "up_sample_steps": [4, 4, 4, 4], "depth_res_levels": [4, 2, 2, 1]}),
+        "implicit_surface": default_implicit_surface_conf()})
+    torch.manual_seed(weight_seed)
+    model = ref_surf.SuRF(model_conf).eval()
+    model.reg_network = standin_reg.StandinReg()
+    near_fars = torch.stack([torch.tensor([float(sc.near), float(sc.far)])] * nv)
+    ipts = {"imgs": sc.imgs, "intrs": sc.intrs, "c2ws": sc.c2ws, "near": sc.near, "far": sc.far, "near_fars": near_fars,
+            "src_idx": 1}
+    with torch.no_grad():
+        features = model.feature_network(sc.imgs)
+        outputs, volumes, idxs, masks, matching = model.build_volumes(ipts, features, False)
+    out = {"matching_volume": matching}
+    for s in range(4):
+        out["volume%d" % s] = volumes[s]
+        out["sparse_idx%d" % s] = idxs[s].to(torch.int32)
+        out["mask%d" % s] = masks[s].to(torch.uint8)
+        out["depth_stage%d" % s] = outputs["depth_stage%d" % s]
+        out["depth_src_stage%d" % s] = outputs["depth_src_stage%d" % s]
+    recipe = dict(nv=nv, H=H, W=W, base=base, scene_seed=scene_seed, weight_seed=weight_seed, scene_sha=scene_checksum(sc))
+
+    class _Nets:
+        def state_dict(self_inner):
+            d = {"feature_network." + k: v for k, v in model.feature_network.state_dict().items()}
+            d.update({"volume." + k: v for k, v in model.volume.state_dict().items()})
+            return d
+    save(name, recipe, _Nets(), {"features%d" % i: f for i, f in enumerate(features)}, out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     IS = ref_loader.load_reference()
@@ -282,6 +342,8 @@ def main():
     case_volume(IS, "volume", nv=3, H=48, W=64, base=8, scene_seed=1, weight_seed=4)
     # I: the 2-D feature pyramid (first half)
     case_fpn(IS, "fpn", nv=2, H=40, W=56, weight_seed=5, img_seed=6)
+    # J: the four-stage volume construction around a stand-in regulariser (A13: SuRF.init_volumes / build_volumes)
+    case_build_volumes(IS, "build_volumes", nv=3, H=48, W=64, base=8, scene_seed=1, weight_seed=8)
 
 
 if __name__ == "__main__":

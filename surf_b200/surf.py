@@ -16,6 +16,8 @@ import torch.nn as nn
 
 from .modules.feature_network import FeatureNetwork
 from .modules.implicit_surface import ImplicitSurface
+from .modules.matching_field import MatchingField
+from .modules.volume import Volume
 
 
 class SuRF(nn.Module):
@@ -27,6 +29,12 @@ class SuRF(nn.Module):
         self.implicit_surface = ImplicitSurface(confs["implicit_surface"])
         # same attribute name as the reference (surf.py:25), so `feature_network.*` checkpoint keys load
         self.feature_network = FeatureNetwork(confs["feature_network"]) if "feature_network" in confs else None
+        self.volume = Volume(confs["volume"]) if "volume" in confs else None
+        self.matching_field = MatchingField(confs["matching_field"]) if "matching_field" in confs else None
+        # The cost-volume regularisation network is the one piece of build_volumes that is not built here (torchsparse,
+        # SURVEY §8f F4).  Plug one in: a callable (feats (n, c) fp32, coords (n, 4) int32 [batch, x, y, z], stage) ->
+        # (out_feats (n, 8), mid_feats (n, d_base)); `TorchsparseRegNetwork` adapts the reference's module.
+        self.reg_network = None
         self.volumes = None
         self.sparse_idxes = None
         self.mask_volmes = None        # (sic) attribute name of the reference, surf.py:74
@@ -53,11 +61,54 @@ class SuRF(nn.Module):
             raise RuntimeError("this SuRF was built from a conf without a feature_network block")
         return self.feature_network(imgs)
 
+    def _upstream_ready(self):
+        missing = [n for n in ("feature_network", "volume", "matching_field", "reg_network") if getattr(self, n) is None]
+        if missing:
+            raise NotImplementedError(
+                "SuRF.build_volumes needs %s; the torchsparse cost-volume regularisation network (reg_network.py) is not "
+                "part of surf_b200 — assign `model.reg_network` (e.g. TorchsparseRegNetwork(reference_module)) or build "
+                "the volumes with the reference and pass them to set_volumes()" % ", ".join(missing))
+
+    @torch.no_grad()
+    def build_volumes(self, ipts, features, perturb=False):
+        """The coarse-to-fine volume construction of surf.py:80-131 on the kernels of Volume / MatchingField, with the
+        regularisation network supplied by the caller.  Same returns: (outputs with depth_stage{s} / depth_src_stage{s},
+        volumes_all, sparse_idx_all, mask_volumes_all, matching_volume), lists coarse -> fine."""
+        self._upstream_ready()
+        intrs, c2ws = ipts["intrs"], ipts["c2ws"]
+        base_range = (ipts["far"] - ipts["near"]).squeeze()
+        vol = self.volume
+        volumes_all, sparse_idx_all, mask_volumes_all = [], [], []
+        depths, matching_volume, coords, carried = None, None, None, None
+        outputs = {}
+        for s in range(self.num_stage):
+            if s == 0:
+                coords = vol.init_coords().to(intrs)
+                up_feats = None
+            else:
+                coords, up_feats = vol.up_sample(coords, carried)
+                coords, up_feats = vol.depth_filtering(depths, coords, up_feats, intrs, c2ws,
+                                                       base_range * self.range_ratios[s])
+            feats, in_frustum = vol.back_proj_multiscale(features, coords, intrs, c2ws, s)
+            feats, coords = feats[in_frustum], coords[in_frustum]
+            if up_feats is not None:
+                feats = torch.cat([feats, up_feats[in_frustum]], dim=1)
+            batched = torch.cat([torch.zeros_like(coords[:, :1]), coords], dim=1).to(torch.int32)     # batch first (:112)
+            out_feats, carried = self.reg_network(feats, batched, s)
+            matching_volume, mask_volume = vol.sparse2dense(out_feats[:, :1], coords, matching_volume)
+            volumes_all.append(out_feats[:, 1:])
+            sparse_idx_all.append(vol.get_index(coords))
+            mask_volumes_all.append(mask_volume)
+            depths, _ = self.matching_field(ipts, matching_volume, s, self.range_ratios, depths, perturb=perturb)
+            outputs["depth_stage%d" % s] = depths[0]
+            outputs["depth_src_stage%d" % s] = depths[ipts["src_idx"]] if "src_idx" in ipts else depths[0]
+        return outputs, volumes_all, sparse_idx_all, mask_volumes_all, matching_volume
+
     def init_volumes(self, ipts):
-        raise NotImplementedError(
-            "SuRF.init_volumes runs the upstream FPN + torchsparse volume construction (surf.py:65-131), which is "
-            "outside the B200 hot path (SURVEY.md §8); build the volumes with the reference and pass them to "
-            "set_volumes()")
+        """surf.py:65-78: features + volumes of a scene from its images; afterwards forward() renders."""
+        features = self.extract_features(ipts["imgs"])               # coarse to fine
+        _, volumes, sparse_idxes, mask_volumes, matching_volume = self.build_volumes(ipts, features, False)
+        self.set_volumes(volumes, sparse_idxes, mask_volumes, matching_volume, features)
 
     def forward(self, mode, ipts, cos_anneal_ratio=1.0, step=None):
         if not self.has_vol:
@@ -71,3 +122,15 @@ class SuRF(nn.Module):
         # lists reversed to fine -> coarse / high-res -> low-res, exactly as surf.py:159
         return self.implicit_surface(mode, ipts, self.matching_volume, self.volumes[::-1], self.sparse_idxes[::-1],
                                      self.mask_volmes[::-1], feats[::-1], feats[::-1], cos_anneal_ratio, step)
+
+
+class TorchsparseRegNetwork:
+    """Adapter for the reference's ``SparseCostRegNetList`` (models/modules/reg_network.py:87-106; needs torchsparse):
+    ``model.reg_network = TorchsparseRegNetwork(reference_reg_network)``."""
+
+    def __init__(self, module):
+        from torchsparse.tensor import SparseTensor        # raises where torchsparse is not installed
+        self._sparse_tensor, self._module = SparseTensor, module
+
+    def __call__(self, feats, coords, stage):
+        return self._module(self._sparse_tensor(feats=feats, coords=coords), stage)
