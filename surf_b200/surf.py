@@ -29,6 +29,11 @@ class SuRF(nn.Module):
         self.implicit_surface = ImplicitSurface(confs["implicit_surface"])
         # same attribute name as the reference (surf.py:25), so `feature_network.*` checkpoint keys load
         self.feature_network = FeatureNetwork(confs["feature_network"]) if "feature_network" in confs else None
+        # the frozen copy the reference renders the matching features with (surf.py:30-32, 141-148)
+        self.match_feature_network = FeatureNetwork(confs["feature_network"]) if "feature_network" in confs else None
+        if self.match_feature_network is not None:
+            for p in self.match_feature_network.parameters():
+                p.requires_grad = False
         self.volume = Volume(confs["volume"]) if "volume" in confs else None
         self.matching_field = MatchingField(confs["matching_field"]) if "matching_field" in confs else None
         # The cost-volume regularisation network is the one piece of build_volumes that is not built here (torchsparse,
@@ -111,17 +116,30 @@ class SuRF(nn.Module):
         self.set_volumes(volumes, sparse_idxes, mask_volumes, matching_volume, features)
 
     def forward(self, mode, ipts, cos_anneal_ratio=1.0, step=None):
+        outputs = {}
         if not self.has_vol:
-            raise NotImplementedError(
-                "SuRF.forward without precomputed volumes needs build_volumes (surf.py:80-131), which is upstream of "
-                "the B200 hot path (SURVEY.md §8); call set_volumes() first")
-        feats = self.features
-        if "view_ids" in ipts:
-            view_ids = ipts["view_ids"]
-            feats = [f[view_ids] for f in feats]
+            # the generalisable path (surf.py:137-148): pyramid + volumes are rebuilt from the images on every call
+            self._upstream_ready()
+            imgs = ipts["imgs"]
+            feats = self.feature_network(imgs)
+            mf_outputs, volumes, sparse_idxes, mask_volumes, matching_volume = self.build_volumes(ipts, feats,
+                                                                                                 perturb=(mode == "train"))
+            outputs.update(mf_outputs)
+            if step is not None and step % 2 == 0:
+                self.match_feature_network.load_state_dict(self.feature_network.state_dict(), strict=True)
+            match_feats = self.match_feature_network(imgs)
+        else:
+            volumes, sparse_idxes, mask_volumes = self.volumes, self.sparse_idxes, self.mask_volmes
+            matching_volume = self.matching_volume
+            feats = self.features
+            if "view_ids" in ipts:
+                view_ids = ipts["view_ids"]
+                feats = [f[view_ids] for f in feats]
+            match_feats = feats
         # lists reversed to fine -> coarse / high-res -> low-res, exactly as surf.py:159
-        return self.implicit_surface(mode, ipts, self.matching_volume, self.volumes[::-1], self.sparse_idxes[::-1],
-                                     self.mask_volmes[::-1], feats[::-1], feats[::-1], cos_anneal_ratio, step)
+        outputs.update(self.implicit_surface(mode, ipts, matching_volume, volumes[::-1], sparse_idxes[::-1],
+                                             mask_volumes[::-1], feats[::-1], match_feats[::-1], cos_anneal_ratio, step))
+        return outputs
 
 
 class TorchsparseRegNetwork:

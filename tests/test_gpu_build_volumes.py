@@ -91,3 +91,29 @@ def test_init_volumes_then_render():
     torch.manual_seed(0)
     out = model("train", ipts)
     assert out["color_fine"].shape == (64, 3) and bool(torch.isfinite(out["color_fine"]).all())
+
+
+def test_forward_without_volumes_rebuilds_them_per_call():
+    """The generalisable branch of SuRF.forward (surf.py:137-148): pyramid + volumes from ipts["imgs"] on every call,
+    the matching-field depth maps in the outputs; same render as init_volumes() followed by the has_vol branch."""
+    g = load_golden("build_volumes")
+    sc = scene_from_recipe(g["recipe"])
+    model = _model(int(g["recipe"]["base"])).to(DEV)
+    model.reg_network = standin_reg.StandinReg()
+    model.match_feature_network.load_state_dict(model.feature_network.state_dict())
+    d = sc.to(DEV)
+    near_fars = torch.stack([torch.tensor([float(sc.near), float(sc.far)])] * sc.nv)
+    from surf_b200 import synthetic
+    o, dd = synthetic.random_pixel_rays(sc, 96, seed=4)
+    ipts = {"imgs": d.imgs, "intrs": d.intrs, "c2ws": d.c2ws, "near": d.near, "far": d.far, "near_fars": near_fars,
+            "src_idx": 1, "rays_o": o.to(DEV), "rays_d": dd.to(DEV)}
+    torch.manual_seed(1)
+    a = model("test", ipts)         # any mode but "train": the matching field is not jittered (surf.py:139)
+    assert not model.has_vol
+    assert all(("depth_stage%d" % s) in a and ("depth_src_stage%d" % s) in a for s in range(4))
+    assert tuple(a["depth_stage3"].shape) == (sc.H, sc.W)
+    model.init_volumes(ipts)
+    torch.manual_seed(1)
+    b = model("test", ipts)
+    for k in ("color_fine", "render_depth", "sdf_depth"):
+        assert torch.equal(torch.as_tensor(a[k]), torch.as_tensor(b[k])), k
