@@ -499,7 +499,10 @@ class ImplicitSurface(nn.Module):
         if near.shape[0] == 1:
             near = near.repeat(rays_o.shape[0], 1)
             far = far.repeat(rays_o.shape[0], 1)
-        scene = self.prepare(matching_volume, volumes, sparse_idxes, mask_volumes, imgs, features, intrs, c2ws)
+        if isinstance(matching_volume, PreparedScene):      # a scene built in the compact layout (Volume.to_prepared_scene)
+            scene = matching_volume.set_views(imgs, features, intrs, c2ws)
+        else:
+            scene = self.prepare(matching_volume, volumes, sparse_idxes, mask_volumes, imgs, features, intrs, c2ws)
         if mode == "val":
             # the reference hard-wires extract_geometry=True, mesh_resolution=512, threshold=0 here (:416-418);
             # ``val_options`` (set by surf_b200.runner.validate) may override them, e.g. a smaller mesh for previews

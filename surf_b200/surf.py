@@ -45,6 +45,7 @@ class SuRF(nn.Module):
         self.mask_volmes = None        # (sic) attribute name of the reference, surf.py:74
         self.matching_volume = None
         self.features = None
+        self.prepared = None           # init_volumes(compact=True): the scene in the prepared layout, no reference tensors
 
     def get_optim_params(self, lr_conf):
         return [{"params": list(self.implicit_surface.parameters()), "lr": lr_conf["mlp_lr"]}]
@@ -58,6 +59,7 @@ class SuRF(nn.Module):
         self.mask_volmes = list(mask_volumes_all)
         self.matching_volume = matching_volume
         self.features = list(features)
+        self.prepared = None
         self.has_vol = True
 
     def extract_features(self, imgs):
@@ -75,16 +77,20 @@ class SuRF(nn.Module):
                 "the volumes with the reference and pass them to set_volumes()" % ", ".join(missing))
 
     @torch.no_grad()
-    def build_volumes(self, ipts, features, perturb=False):
+    def build_volumes(self, ipts, features, perturb=False, compact=False):
         """The coarse-to-fine volume construction of surf.py:80-131 on the kernels of Volume / MatchingField, with the
         regularisation network supplied by the caller.  Same returns: (outputs with depth_stage{s} / depth_src_stage{s},
-        volumes_all, sparse_idx_all, mask_volumes_all, matching_volume), lists coarse -> fine."""
+        volumes_all, sparse_idx_all, mask_volumes_all, matching_volume), lists coarse -> fine.
+        ``compact=True``: the int64 index tables and fp32 mask volumes of the reference layout (6 GB at 704^3, 45 GB at
+        1408^3) are never built; returns (outputs, PreparedScene) with the scene in the renderer's own layout (int32
+        index, 1-bit masks) straight from the per-level voxel lists."""
         self._upstream_ready()
         intrs, c2ws = ipts["intrs"], ipts["c2ws"]
         base_range = (ipts["far"] - ipts["near"]).squeeze()
         vol = self.volume
         volumes_all, sparse_idx_all, mask_volumes_all = [], [], []
         depths, matching_volume, coords, carried = None, None, None, None
+        coords_all, logits_all, dims_all = [], [], []
         outputs = {}
         for s in range(self.num_stage):
             if s == 0:
@@ -101,17 +107,33 @@ class SuRF(nn.Module):
             batched = torch.cat([torch.zeros_like(coords[:, :1]), coords], dim=1).to(torch.int32)     # batch first (:112)
             out_feats, carried = self.reg_network(feats, batched, s)
             matching_volume, mask_volume = vol.sparse2dense(out_feats[:, :1], coords, matching_volume)
-            volumes_all.append(out_feats[:, 1:])
-            sparse_idx_all.append(vol.get_index(coords))
-            mask_volumes_all.append(mask_volume)
+            volumes_all.append(out_feats[:, 1:].contiguous())
+            if compact:
+                del mask_volume
+                coords_all.append(coords.clone())
+                logits_all.append(out_feats[:, :1].contiguous())
+                dims_all.append(int(vol.volume_dim[0]))
+            else:
+                sparse_idx_all.append(vol.get_index(coords))
+                mask_volumes_all.append(mask_volume)
             depths, _ = self.matching_field(ipts, matching_volume, s, self.range_ratios, depths, perturb=perturb)
             outputs["depth_stage%d" % s] = depths[0]
             outputs["depth_src_stage%d" % s] = depths[ipts["src_idx"]] if "src_idx" in ipts else depths[0]
+        if compact:
+            return outputs, Volume.to_prepared_scene(coords_all, volumes_all, logits_all, dims_all)
         return outputs, volumes_all, sparse_idx_all, mask_volumes_all, matching_volume
 
-    def init_volumes(self, ipts):
-        """surf.py:65-78: features + volumes of a scene from its images; afterwards forward() renders."""
+    def init_volumes(self, ipts, compact=False):
+        """surf.py:65-78: features + volumes of a scene from its images; afterwards forward() renders.
+        ``compact=True`` keeps the scene only in the renderer's prepared layout (see build_volumes)."""
         features = self.extract_features(ipts["imgs"])               # coarse to fine
+        if compact:
+            _, scene = self.build_volumes(ipts, features, False, compact=True)
+            self.volumes = self.sparse_idxes = self.mask_volmes = self.matching_volume = None
+            self.features = list(features)
+            self.prepared = scene
+            self.has_vol = True
+            return
         _, volumes, sparse_idxes, mask_volumes, matching_volume = self.build_volumes(ipts, features, False)
         self.set_volumes(volumes, sparse_idxes, mask_volumes, matching_volume, features)
 
@@ -129,9 +151,15 @@ class SuRF(nn.Module):
                 self.match_feature_network.load_state_dict(self.feature_network.state_dict(), strict=True)
             match_feats = self.match_feature_network(imgs)
         else:
+            feats = self.features
+            if self.prepared is not None:        # compact scene: only the views change per call
+                if "view_ids" in ipts:
+                    feats = [f[ipts["view_ids"]] for f in feats]
+                outputs.update(self.implicit_surface(mode, ipts, self.prepared, None, None, None, feats[::-1], feats[::-1],
+                                                     cos_anneal_ratio, step))
+                return outputs
             volumes, sparse_idxes, mask_volumes = self.volumes, self.sparse_idxes, self.mask_volmes
             matching_volume = self.matching_volume
-            feats = self.features
             if "view_ids" in ipts:
                 view_ids = ipts["view_ids"]
                 feats = [f[view_ids] for f in feats]

@@ -117,3 +117,29 @@ def test_forward_without_volumes_rebuilds_them_per_call():
     b = model("test", ipts)
     for k in ("color_fine", "render_depth", "sdf_depth"):
         assert torch.equal(torch.as_tensor(a[k]), torch.as_tensor(b[k])), k
+
+
+def test_compact_init_volumes_renders_the_same():
+    """init_volumes(compact=True): the scene goes straight into the prepared layout (no int64 tables / fp32 masks) and
+    renders bit-identically to the reference-layout path."""
+    g = load_golden("build_volumes")
+    sc = scene_from_recipe(g["recipe"])
+    d = sc.to(DEV)
+    near_fars = torch.stack([torch.tensor([float(sc.near), float(sc.far)])] * sc.nv)
+    from surf_b200 import synthetic
+    o, dd = synthetic.random_pixel_rays(sc, 96, seed=5)
+    ipts = {"imgs": d.imgs, "intrs": d.intrs, "c2ws": d.c2ws, "near": d.near, "far": d.far, "near_fars": near_fars,
+            "src_idx": 1, "rays_o": o.to(DEV), "rays_d": dd.to(DEV)}
+    outs = []
+    for compact in (False, True):
+        torch.manual_seed(11)
+        model = _model(int(g["recipe"]["base"])).to(DEV)
+        model.reg_network = standin_reg.StandinReg()
+        model.init_volumes(ipts, compact=compact)
+        assert model.has_vol and (model.prepared is not None) == compact
+        if compact:
+            assert model.volumes is None and model.sparse_idxes is None
+        torch.manual_seed(2)
+        outs.append(model("train", ipts))
+    for k in ("color_fine", "render_depth", "sdf_depth", "gradients", "weights"):
+        assert torch.equal(outs[0][k], outs[1][k]), k
